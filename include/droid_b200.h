@@ -1,0 +1,124 @@
+/*
+ * droid_b200.h -- C ABI of the B200-native (sm_100a) dense-BA update hot path of DROID-SLAM.
+ *
+ * This is the drop-in boundary: every entry point takes plain device pointers, extents, a dtype code and a
+ * CUDA stream, and returns an int status (0 = ok).  No torch types cross it.  The Python extension
+ * `droid_backends` (droid_slam_b200/csrc/binding/droid_backends.cpp) is a thin pybind11 layer that forwards the
+ * reference's nine callables (reference src/droid.cpp:246-259) to these functions.
+ *
+ * All pointers are DEVICE pointers on the current CUDA device unless stated otherwise.  All tensors are dense
+ * row-major ("contiguous") exactly as the reference requires (src/droid.cpp:89-90).
+ * Index tensors are int64 (reference `LongType`, src/droid_kernels.cu:19-24).
+ */
+#ifndef DROID_B200_H
+#define DROID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dba_stream_t; /* a cudaStream_t */
+
+/* dtype codes for the correlation ops (reference dispatch: AT_DISPATCH_FLOATING_TYPES_AND_HALF,
+ * src/correlation_kernels.cu:146, src/altcorr_kernel.cu:150; bf16 is an extension) */
+enum { DBA_F32 = 0, DBA_F16 = 1, DBA_F64 = 2, DBA_BF16 = 3 };
+
+/* status codes */
+enum {
+  DBA_OK = 0,
+  DBA_ERR_INVALID = 1,   /* bad argument (null pointer, negative extent, unsupported dtype/radius) */
+  DBA_ERR_CUDA = 2,      /* a CUDA runtime call or launch failed; see dba_last_error() */
+  DBA_ERR_WORKSPACE = 3  /* workspace too small */
+};
+
+const char* dba_last_error(void);   /* thread-local, human readable */
+int dba_version(void);              /* 100 * major + minor */
+
+/* ---- correlation volume lookup ------------------------------------------------------------------
+ * replaces corr_index_cuda_forward / corr_index_cuda_backward (reference src/correlation_kernels.cu:127-185,
+ * bound at src/droid.cpp:175-196).
+ * volume [n,h1,w1,h2,w2], coords [n,2,h1,w1] f32, corr [n,2r+1,2r+1,h1,w1] (x-offset major), dtype of volume.
+ * forward fully overwrites `corr`; backward fully overwrites `volume_grad`. */
+int dba_corr_index_forward(const void* volume, const float* coords, void* corr,
+                           int n, int h1, int w1, int h2, int w2, int radius, int dtype, dba_stream_t stream);
+int dba_corr_index_backward(const float* coords, const void* corr_grad, void* volume_grad,
+                            int n, int h1, int w1, int h2, int w2, int radius, int dtype, dba_stream_t stream);
+
+/* ---- on-the-fly correlation ---------------------------------------------------------------------
+ * replaces altcorr_cuda_forward / altcorr_cuda_backward (reference src/altcorr_kernel.cu:132-225, bound at
+ * src/droid.cpp:198-226).
+ * fmap1 [B,N1,C,H,W], fmap2 [B,N2,C,H2,W2], coords [B,M,2,H,W] f32, ii,jj [M] int64 (frame indices into
+ * fmap1 / fmap2).  forward writes `out` as a CONTIGUOUS [B,M,2r+1(y-off),2r+1(x-off),H,W] tensor; the binding
+ * returns its permute(0,1,3,2,4,5) view like the reference (:171).
+ * backward consumes corr_grad [B,M,2r+2,2r+2,H,W] f32 (raw-window gradient, what the reference kernel reads)
+ * and fully overwrites fmap1_grad / fmap2_grad. */
+int dba_altcorr_forward(const void* fmap1, const void* fmap2, const float* coords,
+                        const int64_t* ii, const int64_t* jj, void* out,
+                        int B, int N1, int N2, int C, int H, int W, int H2, int W2, int M,
+                        int radius, int dtype, dba_stream_t stream);
+int dba_altcorr_backward(const void* fmap1, const void* fmap2, const float* coords, const float* corr_grad,
+                         const int64_t* ii, const int64_t* jj, void* fmap1_grad, void* fmap2_grad,
+                         int B, int N1, int N2, int C, int H, int W, int H2, int W2, int M,
+                         int radius, int dtype, dba_stream_t stream);
+
+/* ---- streaming geometry -------------------------------------------------------------------------
+ * poses [n_poses,7] (tx,ty,tz,qx,qy,qz,qw) f32, disps [n_disps,ht,wd] f32, intrinsics [4] f32 (fx,fy,cx,cy).
+ * replace projmap_cuda / frame_distance_cuda / depth_filter_cuda / iproj_cuda
+ * (reference src/droid_kernels.cu:1447-1550, bound at src/droid.cpp:125-171,228-242). */
+int dba_projmap(const float* poses, const float* disps, const float* intrinsics,
+                const int64_t* ii, const int64_t* jj, float* coords /*[E,ht,wd,3]*/, float* valid /*[E,ht,wd,1]*/,
+                int n_edges, int ht, int wd, dba_stream_t stream);
+int dba_frame_distance(const float* poses, const float* disps, const float* intrinsics,
+                       const int64_t* ii, const int64_t* jj, float* dist /*[K]*/,
+                       int n_pairs, int ht, int wd, float beta, dba_stream_t stream);
+int dba_depth_filter(const float* poses, const float* disps, const float* intrinsics,
+                     const int64_t* ix, const float* thresh, float* counter /*[num,ht,wd]*/,
+                     int num, int n_disps, int ht, int wd, dba_stream_t stream);
+int dba_iproj(const float* poses, const float* disps, const float* intrinsics, float* points /*[n,ht,wd,3]*/,
+              int n, int ht, int wd, dba_stream_t stream);
+
+/* ---- dense bundle adjustment --------------------------------------------------------------------
+ * replaces ba_cuda (reference src/droid_kernels.cu:1323-1443, bound at src/droid.cpp:93-122).
+ * In place on poses [n_frames,7] and disps [n_frames,ht,wd]; disps_sens like disps; targets, weights
+ * [E,2,ht,wd]; eta [M,ht,wd] with M = |unique(ii U [t0,t1))| rows in ascending frame order (or 1 row,
+ * broadcast); ii,jj [E] int64.  Outputs of the LAST Gauss-Newton iteration: dx_out [t1-t0,6], dz_out [M,ht*wd]
+ * (dz_out untouched when motion_only).  Everything runs on `stream` with no host synchronisation.
+ *
+ * The call is split at the one point where a multi-GPU run exchanges data:
+ *   dba_ba_prepare   graph bookkeeping (unique / CSR by source frame), once per call
+ *   dba_ba_build     per-edge blocks + depth elimination -> reduced pose system  Hsys [6P,6P] f64 (full, symmetric),
+ *                    bsys [6P] f64 (edge-sharded runs all-reduce exactly this buffer, 8*(36P^2+6P) bytes)
+ *   dba_ba_solve     damping + Cholesky (fp64) -> dx, back-substitution -> dz, retraction of poses and disps
+ * dba_ba runs prepare + iterations x (build, solve).
+ * workspace: dba_ba_workspace_bytes(); layout is private, the reduced system sits at dba_ba_system_offset(). */
+size_t dba_ba_workspace_bytes(int n_frames, int n_edges, int ht, int wd, int t0, int t1);
+size_t dba_ba_system_offset(int n_frames, int n_edges, int ht, int wd, int t0, int t1);  /* bytes from workspace start */
+size_t dba_ba_system_bytes(int t0, int t1);                                              /* 8*(36P^2+6P) */
+
+typedef struct {
+  float* poses; float* disps; const float* intrinsics; const float* disps_sens;
+  const float* targets; const float* weights; const float* eta; int eta_rows;
+  const int64_t* ii; const int64_t* jj;
+  int n_frames, n_edges, ht, wd, t0, t1;
+  float lm, ep; int motion_only;
+  float* dx_out; float* dz_out;
+  void* workspace; size_t workspace_bytes;
+  dba_stream_t stream;
+} dba_ba_args;
+
+int dba_ba_prepare(const dba_ba_args* a);
+int dba_ba_build(const dba_ba_args* a);
+int dba_ba_solve(const dba_ba_args* a);
+int dba_ba(const dba_ba_args* a, int iterations);
+/* synchronises `stream` and reads back M = number of depth frames found by the last dba_ba_prepare on this
+ * workspace and the sticky device status word (0 = ok, bit0 = index out of range, bit1 = eta rows != M,
+ * bit2 = Cholesky hit a non-positive pivot in some iteration -> that iteration's dx = 0 like the reference). */
+int dba_ba_read_info(const dba_ba_args* a, int* n_depth_frames, int* device_status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DROID_B200_H */
