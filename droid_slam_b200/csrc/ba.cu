@@ -1,0 +1,933 @@
+// Dense bundle adjustment (Gauss-Newton, Schur complement over per-pixel inverse depth) for sm_100a.
+//
+// Replaces reference src/droid_kernels.cu:185-433 (K1), :863-1124 (accum / retraction / Schur kernels),
+// :1126-1320 (CPU SparseBlock + schur_block) and the driver :1323-1443.  Same maths, different machine mapping:
+//
+//   * everything stays on the device and on one stream: no .to(kCPU), no argsort/CSR on the host, no Eigen;
+//   * edges are grouped by SOURCE frame (CSR built once per call by two small kernels).  One CTA owns
+//     (depth frame k, pixel chunk): it walks the out-edges of k, so the depth-block sums C_k, w_k, Ei_k are plain
+//     register accumulations (no atomics, no segmented-sum kernels, deterministic);
+//   * only Hjj (21 unique) and vj (6) are accumulated per pixel.  Ji = -Adj^T(G_ij) Jj is linear in Jj, hence
+//     Hii = A Hjj A^T, Hij = -A Hjj, vi = -A vj are formed once per edge from the reduced fp64 sums
+//     (the reference accumulates all 78+12 sums per pixel and does 90 serial block reductions);
+//   * reductions: fp32 per thread over its pixels -> warp shuffles -> fp64 across warps -> fp64 atomics into the
+//     dense reduced system Hsys [6P x 6P] / bsys [6P] (this is the buffer an edge-sharded multi-GPU run all-reduces);
+//   * the Schur complement S = sum_k E_k Q_k E_k^T is a per-frame SYRK over the (1+deg_k) rows of frame k with the
+//     6x6 block pairs register-tiled per thread (the reference enumerates (i,j,k) triples on the CPU, O(P^2 deg^2));
+//   * solve: damping (diag += ep + lm*diag) and a tiled fp64 Cholesky on the device; a non-positive pivot gives
+//     dx = 0 like the reference's `solver.info() != Success` branch;
+//   * back-substitution dz = Q (w - E^T dx) keeps the reference quirk Q9 (rows whose pose index is <= 0 are skipped,
+//     src/droid_kernels.cu:1114), then retraction of poses (left-multiplicative Exp, no renormalisation) and disps.
+#include "common.cuh"
+#include <math.h>
+
+namespace dba {
+
+constexpr int kPPT = 4;            // pixels per thread in the build kernel
+constexpr int kBuildThreads = 256;
+constexpr int kChunkPx = kPPT * kBuildThreads;   // 1024 pixels per CTA
+constexpr int kEdgeBatch = 16;     // edges whose transforms / partial sums live in shared memory at once
+constexpr int kTile = 32;          // Cholesky tile
+
+struct Layout {
+  size_t off_hdr, off_frame2k, off_kx, off_rowptr, off_edgeidx, off_sys, off_L, off_dx, off_Eij, off_C, off_w, off_Ei, total;
+  int P, n;
+};
+
+__host__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ inline Layout make_layout(int N, int E, int ht, int wd, int t0, int t1) {
+  Layout L;
+  const size_t HW = (size_t)ht * wd;
+  L.P = t1 - t0 > 0 ? t1 - t0 : 0;
+  L.n = 6 * L.P;
+  const size_t npad = (size_t)((L.n + kTile - 1) / kTile) * kTile;
+  size_t o = 0;
+  L.off_hdr = o;      o = align_up(o + 64 * sizeof(int), 256);
+  L.off_frame2k = o;  o = align_up(o + (size_t)(N + 1) * sizeof(int), 256);
+  L.off_kx = o;       o = align_up(o + (size_t)(N + 1) * sizeof(int), 256);
+  L.off_rowptr = o;   o = align_up(o + (size_t)(N + 2) * sizeof(int), 256);
+  L.off_edgeidx = o;  o = align_up(o + (size_t)(E + 1) * sizeof(int), 256);
+  L.off_sys = o;      o = align_up(o + ((size_t)L.n * L.n + L.n) * sizeof(double), 256);
+  L.off_L = o;        o = align_up(o + (npad * npad + 2 * npad) * sizeof(double), 256);
+  L.off_dx = o;       o = align_up(o + (size_t)(L.n + 6) * sizeof(float), 256);
+  L.off_Eij = o;      o = align_up(o + (size_t)E * 6 * HW * sizeof(float), 256);
+  const size_t Mmax = (size_t)N;   // at most one depth frame per buffer frame
+  L.off_C = o;        o = align_up(o + Mmax * HW * sizeof(float), 256);
+  L.off_w = o;        o = align_up(o + Mmax * HW * sizeof(float), 256);
+  L.off_Ei = o;       o = align_up(o + Mmax * 6 * HW * sizeof(float), 256);
+  L.total = o;
+  return L;
+}
+
+// header words
+enum { HDR_STATUS = 0, HDR_M = 1, HDR_CHOL_FAIL = 2 };
+enum { ST_BAD_INDEX = 1, ST_ETA_ROWS = 2, ST_CHOL_FAIL = 4 };
+
+// ---------------------------------------------------------------------------------------------------------
+// prepare: kx = sorted unique(ii U [t0,t1)), frame2k, CSR of edges by source frame (stable in edge order)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ba_prepare_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int E, int N,
+                                                          int t0, int t1, int eta_rows, int* __restrict__ hdr,
+                                                          int* __restrict__ frame2k, int* __restrict__ kx, int* __restrict__ rowptr) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x;
+  if (tid == 0) { hdr[HDR_STATUS] = 0; hdr[HDR_CHOL_FAIL] = 0; }
+  for (int f = tid; f < N; f += blockDim.x) { frame2k[f] = (f >= t0 && f < t1) ? 1 : 0; rowptr[f] = 0; }
+  if (tid == 0) { rowptr[N] = 0; rowptr[N + 1] = 0; }
+  __syncthreads();
+  for (int e = tid; e < E; e += blockDim.x) {
+    const long long i = ii[e], j = jj[e];
+    if (i < 0 || i >= N || j < 0 || j >= N) { atomicOr(&hdr[HDR_STATUS], ST_BAD_INDEX); continue; }
+    frame2k[i] = 1;
+  }
+  __syncthreads();
+  // exclusive scan of the presence flags -> dense index
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += blockDim.x) {
+    const int f = base + tid;
+    const int flag = (f < N) ? frame2k[f] : 0;
+    s_scan[tid] = flag;
+    __syncthreads();
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+      int v = (tid >= off) ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    const int incl = s_scan[tid];
+    const int idx = s_carry + incl - flag;
+    if (f < N) {
+      frame2k[f] = flag ? idx : -1;
+      if (flag) kx[idx] = f;
+    }
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry += incl;
+    __syncthreads();
+  }
+  const int M = s_carry;
+  if (tid == 0) {
+    hdr[HDR_M] = M;
+    if (eta_rows != M && eta_rows != 1) atomicOr(&hdr[HDR_STATUS], ST_ETA_ROWS);
+  }
+  // out-degree per depth frame -> rowptr (exclusive scan, serial per chunk is fine: M <= N small)
+  for (int e = tid; e < E; e += blockDim.x) {
+    const long long i = ii[e], j = jj[e];
+    if (i < 0 || i >= N || j < 0 || j >= N) continue;
+    atomicAdd(&rowptr[frame2k[i] + 1], 1);
+  }
+  __syncthreads();
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base <= M; base += blockDim.x) {
+    const int m = base + tid;
+    const int cnt = (m <= M) ? rowptr[m] : 0;     // rowptr[m] currently holds deg(m-1), rowptr[0] = 0
+    s_scan[tid] = cnt;
+    __syncthreads();
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+      int v = (tid >= off) ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    if (m <= M) rowptr[m] = s_carry + s_scan[tid];
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry += s_scan[tid];
+    __syncthreads();
+  }
+}
+
+// stable placement of every edge inside its source frame's segment: rank = #earlier edges with the same source
+__global__ void __launch_bounds__(256) ba_fill_csr_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int E, int N,
+                                                          const int* __restrict__ frame2k, const int* __restrict__ rowptr,
+                                                          int* __restrict__ edgeidx) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const long long i = ii[e], j = jj[e];
+  if (i < 0 || i >= N || j < 0 || j >= N) return;
+  int rank = 0;
+  for (int f = 0; f < e; f++) {
+    const long long i2 = ii[f], j2 = jj[f];
+    rank += (i2 == i && j2 >= 0 && j2 < N) ? 1 : 0;
+  }
+  edgeidx[rowptr[frame2k[i]] + rank] = e;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// build: per (depth frame, pixel chunk): geometry of all out-edges, depth-block sums, per-edge pose blocks
+// ---------------------------------------------------------------------------------------------------------
+struct EdgeSm {
+  float t[3], q[4];      // G_ij
+  float A[36];           // Ji = -A Jj   (A = transposed adjoint, applied with the reference's adjSE3 arithmetic)
+  int e, jx, stereo;
+};
+
+// Y = adjSE3(t,q,X)  (reference src/droid_kernels.cu:88-103)
+__device__ __forceinline__ void adj_se3(const float* t, const float* q, const float* X, float* Y) {
+  float qinv[4] = {-q[0], -q[1], -q[2], q[3]};
+  act_so3(qinv, X, Y);
+  act_so3(qinv, X + 3, Y + 3);
+  float u[3], v[3];
+  u[0] = t[2] * X[1] - t[1] * X[2];
+  u[1] = t[0] * X[2] - t[2] * X[0];
+  u[2] = t[1] * X[0] - t[0] * X[1];
+  act_so3(qinv, u, v);
+  Y[3] += v[0]; Y[4] += v[1]; Y[5] += v[2];
+}
+
+__global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
+    const float* __restrict__ poses, const float* __restrict__ disps, const float* __restrict__ intr,
+    const float* __restrict__ disps_sens, const float* __restrict__ targets, const float* __restrict__ weights,
+    const float* __restrict__ eta, int eta_rows, const int64_t* __restrict__ jj,
+    const int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr, const int* __restrict__ edgeidx,
+    int HW, int wd, int t0, int P, int motion_only,
+    double* __restrict__ Hsys, double* __restrict__ bsys, float* __restrict__ Eij, float* __restrict__ Cout, float* __restrict__ wout,
+    float* __restrict__ Eiout) {
+  const int m = blockIdx.y;
+  if (m >= hdr[HDR_M]) return;
+  const int ix = kx[m];
+  const int e_begin = rowptr[m], e_end = rowptr[m + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kBuildThreads / 32;
+
+  __shared__ EdgeSm s_edge[kEdgeBatch];
+  __shared__ float s_part[NW][kEdgeBatch][27];
+  __shared__ double s_sum[kEdgeBatch][27];
+
+  const float fx = __ldg(intr), fy = __ldg(intr + 1), cx = __ldg(intr + 2), cy = __ldg(intr + 3);
+  const int n = 6 * P;
+
+  // this thread's pixels
+  int pix[kPPT];
+  float Xi0[kPPT], Xi1[kPPT], dsp[kPPT];
+  float Cacc[kPPT], wacc[kPPT], Eiacc[kPPT][6];
+#pragma unroll
+  for (int s = 0; s < kPPT; s++) {
+    const int p = blockIdx.x * kChunkPx + s * kBuildThreads + tid;
+    pix[s] = p;
+    const bool ok = p < HW;
+    const int i = ok ? p / wd : 0, j = ok ? p - i * wd : 0;
+    Xi0[s] = ((float)j - cx) / fx;
+    Xi1[s] = ((float)i - cy) / fy;
+    dsp[s] = ok ? __ldg(disps + (size_t)ix * HW + p) : 1.f;
+    Cacc[s] = 0.f; wacc[s] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 6; c++) Eiacc[s][c] = 0.f;
+  }
+
+  for (int eb = e_begin; eb < e_end; eb += kEdgeBatch) {
+    const int nb = min(kEdgeBatch, e_end - eb);
+    __syncthreads();   // previous batch fully consumed
+    // ---- edge transforms + adjoint matrices for the batch
+    if (tid < nb) {
+      EdgeSm& S = s_edge[tid];
+      const int e = edgeidx[eb + tid];
+      S.e = e; S.jx = (int)jj[e]; S.stereo = (S.jx == ix);
+      edge_transform(poses, ix, S.jx, /*stereo_quirk=*/true, S.t, S.q);
+    }
+    __syncthreads();
+    if (tid < nb * 6) {
+      const int b = tid / 6, c = tid - b * 6;
+      float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, Y[6];
+      X[c] = 1.f;
+      adj_se3(s_edge[b].t, s_edge[b].q, X, Y);
+#pragma unroll
+      for (int r = 0; r < 6; r++) s_edge[b].A[r * 6 + c] = Y[r];
+    }
+    __syncthreads();
+
+    for (int b = 0; b < nb; b++) {
+      const EdgeSm& S = s_edge[b];
+      const float t0_ = S.t[0], t1_ = S.t[1], t2_ = S.t[2];
+      const int e = S.e;
+      const bool stereo = S.stereo != 0;
+      float Hjj[21], vj[6];
+#pragma unroll
+      for (int k = 0; k < 21; k++) Hjj[k] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 6; k++) vj[k] = 0.f;
+
+#pragma unroll
+      for (int s = 0; s < kPPT; s++) {
+        const int p = pix[s];
+        if (p < HW) {
+          float Xi[4] = {Xi0[s], Xi1[s], 1.f, dsp[s]}, Xj[4];
+          act_se3(S.t, S.q, Xi, Xj);
+          const float x = Xj[0], y = Xj[1], h = Xj[3];
+          const bool close = (double)Xj[2] < 0.25;   // MIN_DEPTH is a double literal in the reference
+          const float d = close ? 0.f : 1.0f / Xj[2];
+          const float d2 = d * d;
+          // `.001 * weight`: fp64 product rounded to fp32 (reference :314-315)
+          float wu = close ? 0.f : (float)(.001 * (double)__ldg(weights + ((size_t)e * 2 + 0) * HW + p));
+          float wv = close ? 0.f : (float)(.001 * (double)__ldg(weights + ((size_t)e * 2 + 1) * HW + p));
+          const float ru = __ldg(targets + ((size_t)e * 2 + 0) * HW + p) - (fx * d * x + cx);
+          const float rv = __ldg(targets + ((size_t)e * 2 + 1) * HW + p) - (fy * d * y + cy);
+          float Ju[6], Jv[6];
+          Ju[0] = fx * (h * d); Ju[1] = fx * 0; Ju[2] = fx * (-x * h * d2);
+          Ju[3] = fx * (-x * y * d2); Ju[4] = fx * (1 + x * x * d2); Ju[5] = fx * (-y * d);
+          Jv[0] = fy * 0; Jv[1] = fy * (h * d); Jv[2] = fy * (-y * h * d2);
+          Jv[3] = fy * (-1 - y * y * d2); Jv[4] = fy * (x * y * d2); Jv[5] = fy * (x * d);
+          const float Jzu = fx * (t0_ * d - t2_ * (x * d2));
+          const float Jzv = fy * (t1_ * d - t2_ * (y * d2));
+          Cacc[s] += wu * Jzu * Jzu + wv * Jzv * Jzv;
+          wacc[s] += wu * ru * Jzu + wv * rv * Jzv;
+          if (stereo) { wu = 0.f; wv = 0.f; }       // pose weights vanish AFTER the depth terms (Q1)
+          const float au = wu * Jzu, av = wv * Jzv;
+          float Ej[6];
+#pragma unroll
+          for (int c = 0; c < 6; c++) Ej[c] = au * Ju[c] + av * Jv[c];
+          if (!motion_only) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) Eij[((size_t)e * 6 + c) * HW + p] = Ej[c];
+            // Eii = -A Eij, accumulated over the out-edges of this frame
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+              float acc = 0.f;
+#pragma unroll
+              for (int c = 0; c < 6; c++) acc += S.A[r * 6 + c] * Ej[c];
+              Eiacc[s][r] -= acc;
+            }
+          }
+          const float wru = wu * ru, wrv = wv * rv;
+          int l = 0;
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+            vj[a] += wru * Ju[a] + wrv * Jv[a];
+            const float wa_u = wu * Ju[a], wa_v = wv * Jv[a];
+#pragma unroll
+            for (int c = 0; c <= a; c++) { Hjj[l] += wa_u * Ju[c] + wa_v * Jv[c]; l++; }
+          }
+        }
+      }
+      // warp reduction, one partial per warp
+#pragma unroll
+      for (int k = 0; k < 21; k++) { const float v = warp_sum(Hjj[k]); if (lane == 0) s_part[warp][b][k] = v; }
+#pragma unroll
+      for (int k = 0; k < 6; k++) { const float v = warp_sum(vj[k]); if (lane == 0) s_part[warp][b][21 + k] = v; }
+    }
+    __syncthreads();
+    // ---- cross-warp sums in fp64
+    for (int k = tid; k < nb * 27; k += kBuildThreads) {
+      const int b = k / 27, c = k - b * 27;
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; w++) s += (double)s_part[w][b][c];
+      s_sum[b][c] = s;
+    }
+    __syncthreads();
+    // ---- per edge: Hii = A Hjj A^T, Hij = -A Hjj, Hji = Hij^T, vi = -A vj ; scatter into the reduced system
+    // 156 outputs per edge: 144 matrix entries (4 blocks x 36) + 12 vector entries
+    for (int k = tid; k < nb * 156; k += kBuildThreads) {
+      const int b = k / 156, o = k - b * 156;
+      const EdgeSm& S = s_edge[b];
+      if (S.stereo) continue;                           // all-zero blocks
+      const int pi = ix - t0, pj = S.jx - t0;
+      const double* hs = s_sum[b];
+      auto H = [&](int a, int c) -> double { return (a >= c) ? hs[a * (a + 1) / 2 + c] : hs[c * (c + 1) / 2 + a]; };
+      if (o < 144) {
+        const int blk = o / 36, rc = o - blk * 36, r = rc / 6, c = rc - r * 6;
+        int prow, pcol; double val = 0.0;
+        if (blk == 0) {          // Hii[r][c] = sum_ab A[r][a] Hjj[a][b] A[c][b]
+          prow = pi; pcol = pi;
+          for (int a = 0; a < 6; a++) { double t = 0.0; for (int b2 = 0; b2 < 6; b2++) t += H(a, b2) * (double)S.A[c * 6 + b2]; val += (double)S.A[r * 6 + a] * t; }
+        } else if (blk == 1) {   // Hij[r][c] = -sum_a A[r][a] Hjj[a][c]
+          prow = pi; pcol = pj;
+          for (int a = 0; a < 6; a++) val -= (double)S.A[r * 6 + a] * H(a, c);
+        } else if (blk == 2) {   // Hji[r][c] = Hij[c][r]
+          prow = pj; pcol = pi;
+          for (int a = 0; a < 6; a++) val -= (double)S.A[c * 6 + a] * H(a, r);
+        } else {
+          prow = pj; pcol = pj; val = H(r, c);
+        }
+        if (prow >= 0 && prow < P && pcol >= 0 && pcol < P) atomicAdd(&Hsys[(size_t)(prow * 6 + r) * n + pcol * 6 + c], val);
+      } else {
+        const int v = o - 144, blk = v / 6, r = v - blk * 6;
+        double val = 0.0; int prow;
+        if (blk == 0) { prow = pi; for (int a = 0; a < 6; a++) val -= (double)S.A[r * 6 + a] * hs[21 + a]; }
+        else { prow = pj; val = hs[21 + r]; }
+        if (prow >= 0 && prow < P) atomicAdd(&bsys[prow * 6 + r], val);
+      }
+    }
+  }
+
+  if (!motion_only) {
+    // depth block:  C = sum Cii + m*alpha + (1-m)*eta ;  w = sum bz - m*alpha*(d - d_sens)   (reference :1405-1408)
+    const float alpha = 0.05f;
+    const int erow = (eta_rows == 1) ? 0 : min(m, eta_rows - 1);
+#pragma unroll
+    for (int s = 0; s < kPPT; s++) {
+      const int p = pix[s];
+      if (p < HW) {
+        const float dsn = __ldg(disps_sens + (size_t)ix * HW + p);
+        const float mk = (dsn > 0.f) ? 1.f : 0.f;
+        const float C = Cacc[s] + mk * alpha + (1 - mk) * __ldg(eta + (size_t)erow * HW + p);
+        const float w = wacc[s] - mk * alpha * (dsp[s] - dsn);
+        Cout[(size_t)m * HW + p] = C;
+        wout[(size_t)m * HW + p] = w;
+#pragma unroll
+        for (int c = 0; c < 6; c++) Eiout[((size_t)m * 6 + c) * HW + p] = Eiacc[s][c];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Schur complement:  Hsys -= sum_k E_k Q_k E_k^T ,  bsys -= sum_k E_k Q_k w_k       (reference K9/K10 + schur_block)
+// rows of frame k: row 0 = (pose k, Ei_k) if k in [t0,t1); row 1+a = (pose jj[e_a], Eij[e_a]); rows whose pose is
+// outside [t0,t1) are dropped.  One CTA per (frame, pixel chunk); a thread owns one 6x6 block pair (r <= r').
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSchurThreads = 128;
+constexpr int kSchurTP = 64;        // pixels per shared-memory sub tile
+constexpr int kSchurMaxRows = 24;   // rows per pass; larger out-degrees are processed in several row-block passes
+
+__global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
+    const int64_t* __restrict__ jj, const int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
+    const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
+    const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
+    double* __restrict__ Hsys, double* __restrict__ bsys) {
+  const int m = blockIdx.y;
+  if (m >= hdr[HDR_M]) return;
+  const int ix = kx[m];
+  const int e_begin = rowptr[m];
+  const int deg = rowptr[m + 1] - e_begin;
+  const int tid = threadIdx.x;
+  const int n = 6 * P;
+
+  // active rows (pose inside the window)
+  __shared__ int s_rowpose[kSchurMaxRows * 2];
+  __shared__ const float* s_rowptr[kSchurMaxRows * 2];
+  __shared__ int s_nrows_total;
+  extern __shared__ float s_dyn[];   // [2 row blocks][kSchurTP][stride] + Q[kSchurTP] + Qw[kSchurTP]
+
+  // The row list can be longer than kSchurMaxRows: process row-block pairs (bi <= bj)
+  // First count the active rows.
+  int nrows = 0;
+  {
+    // serial count by thread 0 (deg is small); rows are indexed on the fly by `nth_row`
+    if (tid == 0) {
+      int c = 0;
+      if (ix >= t0 && ix < t0 + P) c++;
+      for (int a = 0; a < deg; a++) { const int pj = (int)jj[edgeidx[e_begin + a]] - t0; if (pj >= 0 && pj < P) c++; }
+      s_nrows_total = c;
+    }
+    __syncthreads();
+    nrows = s_nrows_total;
+  }
+  if (nrows == 0) return;
+  const int nblk = (nrows + kSchurMaxRows - 1) / kSchurMaxRows;
+  const int stride = 6 * kSchurMaxRows + 2;   // even (8-byte aligned LDS.64), != 0 mod 32
+  float* sA = s_dyn;                              // row block bi
+  float* sB = s_dyn + (size_t)kSchurTP * stride;  // row block bj
+  float* sQ = sB + (size_t)kSchurTP * stride;
+  float* sQw = sQ + kSchurTP;
+
+  const int px_begin = blockIdx.x * px_per_cta;
+  const int px_end = min(HW, px_begin + px_per_cta);
+
+  for (int bi = 0; bi < nblk; bi++) {
+    for (int bj = bi; bj < nblk; bj++) {
+      __syncthreads();
+      // ---- resolve the rows of the two blocks (thread 0 walks the list; tiny)
+      if (tid == 0) {
+        int c = 0;
+        auto put = [&](int pose, const float* ptr) {
+          const int blk = c / kSchurMaxRows, pos = c - blk * kSchurMaxRows;
+          if (blk == bi) { s_rowpose[pos] = pose; s_rowptr[pos] = ptr; }
+          if (blk == bj) { s_rowpose[kSchurMaxRows + pos] = pose; s_rowptr[kSchurMaxRows + pos] = ptr; }
+          c++;
+        };
+        if (ix >= t0 && ix < t0 + P) put(ix - t0, Eiin + (size_t)m * 6 * HW);
+        for (int a = 0; a < deg; a++) {
+          const int e = edgeidx[e_begin + a];
+          const int pj = (int)jj[e] - t0;
+          if (pj >= 0 && pj < P) put(pj, Eij + (size_t)e * 6 * HW);
+        }
+      }
+      __syncthreads();
+      const int ra = min(kSchurMaxRows, nrows - bi * kSchurMaxRows);
+      const int rb = min(kSchurMaxRows, nrows - bj * kSchurMaxRows);
+      // pairs: bi == bj -> r <= r' ; else all (r, r')
+      const int npairs = (bi == bj) ? ra * (ra + 1) / 2 : ra * rb;
+      for (int pbase = 0; pbase < npairs; pbase += kSchurThreads) {
+        const int pr = pbase + tid;
+        int r = 0, r2 = 0;
+        const bool active = pr < npairs;
+        if (active) {
+          if (bi == bj) {   // unrank lower-triangular pair index: pr = r2*(r2+1)/2 + r, r <= r2
+            r2 = (int)((sqrtf(8.f * (float)pr + 1.f) - 1.f) * 0.5f);
+            while (r2 * (r2 + 1) / 2 > pr) r2--;
+            while ((r2 + 1) * (r2 + 2) / 2 <= pr) r2++;
+            r = pr - r2 * (r2 + 1) / 2;
+          } else { r = pr / rb; r2 = pr - r * rb; }
+        }
+        float acc[36], bacc[6];
+#pragma unroll
+        for (int k = 0; k < 36; k++) acc[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) bacc[k] = 0.f;
+
+        for (int p0 = px_begin; p0 < px_end; p0 += kSchurTP) {
+          const int np = min(kSchurTP, px_end - p0);
+          __syncthreads();
+          // stage rows: sA[px][row*6+c], sB likewise; Q and Q*w
+          for (int k = tid; k < ra * 6 * kSchurTP; k += kSchurThreads) {
+            const int px = k % kSchurTP, rc = k / kSchurTP;
+            const int row = rc / 6, c = rc - row * 6;
+            sA[px * stride + rc] = (px < np) ? __ldg(s_rowptr[row] + (size_t)c * HW + p0 + px) : 0.f;
+          }
+          if (bj != bi) {
+            for (int k = tid; k < rb * 6 * kSchurTP; k += kSchurThreads) {
+              const int px = k % kSchurTP, rc = k / kSchurTP;
+              const int row = rc / 6, c = rc - row * 6;
+              sB[px * stride + rc] = (px < np) ? __ldg(s_rowptr[kSchurMaxRows + row] + (size_t)c * HW + p0 + px) : 0.f;
+            }
+          }
+          for (int px = tid; px < kSchurTP; px += kSchurThreads) {
+            float q = 0.f, qw = 0.f;
+            if (px < np) { q = 1.0f / __ldg(Cin + (size_t)m * HW + p0 + px); qw = q * __ldg(win + (size_t)m * HW + p0 + px); }
+            sQ[px] = q; sQw[px] = qw;
+          }
+          __syncthreads();
+          if (active) {
+            const float* rowA = sA + r * 6;
+            const float* rowB = ((bi == bj) ? sA : sB) + r2 * 6;
+            for (int px = 0; px < np; px++) {
+              const float q = sQ[px];
+              const float2 a01 = *reinterpret_cast<const float2*>(rowA + px * stride);
+              const float2 a23 = *reinterpret_cast<const float2*>(rowA + px * stride + 2);
+              const float2 a45 = *reinterpret_cast<const float2*>(rowA + px * stride + 4);
+              const float2 b01 = *reinterpret_cast<const float2*>(rowB + px * stride);
+              const float2 b23 = *reinterpret_cast<const float2*>(rowB + px * stride + 2);
+              const float2 b45 = *reinterpret_cast<const float2*>(rowB + px * stride + 4);
+              const float ea[6] = {a01.x * q, a01.y * q, a23.x * q, a23.y * q, a45.x * q, a45.y * q};   // ei[n] = E*q (reference :1039)
+              const float eb[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+#pragma unroll
+              for (int a = 0; a < 6; a++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[a * 6 + c] += ea[a] * eb[c];
+              if (bi == bj && r == r2) {
+                const float qw = sQw[px];
+                bacc[0] += qw * a01.x; bacc[1] += qw * a01.y; bacc[2] += qw * a23.x;
+                bacc[3] += qw * a23.y; bacc[4] += qw * a45.x; bacc[5] += qw * a45.y;
+              }
+            }
+          }
+        }
+        if (active) {
+          const int pa = s_rowpose[r];
+          const int pb = s_rowpose[((bi == bj) ? 0 : kSchurMaxRows) + r2];
+          const bool same_row = (bi == bj) && (r == r2);
+#pragma unroll
+          for (int a = 0; a < 6; a++) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+              const double v = (double)acc[a * 6 + c];
+              atomicAdd(&Hsys[(size_t)(pa * 6 + a) * n + pb * 6 + c], -v);
+              if (!same_row) atomicAdd(&Hsys[(size_t)(pb * 6 + c) * n + pa * 6 + a], -v);
+            }
+          }
+          if (same_row) {
+#pragma unroll
+            for (int a = 0; a < 6; a++) atomicAdd(&bsys[pa * 6 + a], -(double)bacc[a]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// solve: L = Hsys with damping; tiled fp64 Cholesky (single CTA, v1); dx = L^-T L^-1 bsys
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSolveThreads = 256;
+
+// warp-level Cholesky of one 32x32 tile held one row per lane.  Returns false on a non-positive pivot.
+__device__ __forceinline__ bool warp_potrf32(double (&a)[kTile], int lane, int valid) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < kTile; k++) {
+    double d = __shfl_sync(0xffffffffu, a[k], k);
+    if (k >= valid) d = 1.0;            // padding rows/cols behave like identity
+    if (!(d > 0.0)) ok = false;
+    const double l_kk = sqrt(d);
+    const double r = 1.0 / l_kk;
+    const double l = (lane == k) ? l_kk : a[k] * r;   // column k, rows >= k (rows < k hold garbage that is never used)
+    a[k] = l;
+#pragma unroll
+    for (int j = k + 1; j < kTile; j++) {
+      const double ljk = __shfl_sync(0xffffffffu, l, j);
+      a[j] -= l * ljk;                  // only rows >= j matter
+    }
+  }
+  return ok;
+}
+
+__global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(const double* __restrict__ Hsys, const double* __restrict__ bsys,
+                                                                 double* __restrict__ Lbuf, int n, float lm, float ep,
+                                                                 int* __restrict__ hdr, float* __restrict__ dx) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kSolveThreads / 32;
+  const int nt = (n + kTile - 1) / kTile;
+  const int np = nt * kTile;
+  double* L = Lbuf;                       // [np][np] row-major, lower triangle used
+  double* y = Lbuf + (size_t)np * np;     // [np]
+  __shared__ double s_Lkk[kTile][kTile + 1];
+  __shared__ double s_rdiag[kTile];
+  __shared__ int s_fail;
+  if (tid == 0) s_fail = 0;
+
+  // ---- copy lower triangle with damping (reference SparseBlock::solve :1205-1206: diag += ep + lm*diag, in fp64)
+  const double lm64 = (double)lm, ep64 = (double)ep;
+  for (size_t idx = tid; idx < (size_t)np * np; idx += kSolveThreads) {
+    const int r = (int)(idx / np), c = (int)(idx - (size_t)r * np);
+    double v = 0.0;
+    if (r < n && c < n && c <= r) {
+      v = Hsys[(size_t)r * n + c];
+      if (r == c) v += ep64 + lm64 * v;
+    } else if (r == c) v = 1.0;
+    L[idx] = v;
+  }
+  for (int i = tid; i < np; i += kSolveThreads) y[i] = (i < n) ? bsys[i] : 0.0;
+  __syncthreads();
+
+  for (int k = 0; k < nt; k++) {
+    // (a) potrf of the diagonal tile by warp 0
+    if (warp == 0) {
+      double a[kTile];
+#pragma unroll
+      for (int c = 0; c < kTile; c++) a[c] = L[(size_t)(k * kTile + lane) * np + k * kTile + c];
+      const bool ok = warp_potrf32(a, lane, kTile);
+      if (!ok && lane == 0) s_fail = 1;
+#pragma unroll
+      for (int c = 0; c < kTile; c++) {
+        const double v = (c <= lane) ? a[c] : 0.0;
+        s_Lkk[lane][c] = v;
+        L[(size_t)(k * kTile + lane) * np + k * kTile + c] = v;
+      }
+      // reciprocal diagonal: a[lane] of lane `lane`
+      double dg = 0.0;
+#pragma unroll
+      for (int c = 0; c < kTile; c++) if (c == lane) dg = a[c];
+      s_rdiag[lane] = 1.0 / dg;
+    }
+    __syncthreads();
+    if (s_fail) break;
+    // (b) TRSM: tiles (i,k), i > k: one warp per tile, lane = row:  X L_kk^T = A
+    for (int i = k + 1 + warp; i < nt; i += NW) {
+      double a[kTile];
+      double* rowp = L + (size_t)(i * kTile + lane) * np + k * kTile;
+#pragma unroll
+      for (int c = 0; c < kTile; c++) a[c] = rowp[c];
+#pragma unroll
+      for (int c = 0; c < kTile; c++) {
+        const double x = a[c] * s_rdiag[c];
+        a[c] = x;
+#pragma unroll
+        for (int j = c + 1; j < kTile; j++) a[j] -= x * s_Lkk[j][c];
+        asm volatile("" ::: "memory");   // keep the 496 broadcast loads from being hoisted (register spills)
+      }
+#pragma unroll
+      for (int c = 0; c < kTile; c++) rowp[c] = a[c];
+    }
+    __syncthreads();
+    // (c) trailing update: tiles (i,j), k < j <= i:  A_ij -= L_ik L_jk^T ; one warp per tile, lane = row of (i,j)
+    const int rem = nt - k - 1;
+    const int ntiles = rem * (rem + 1) / 2;
+    for (int t = warp; t < ntiles; t += NW) {
+      int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+      while (bi * (bi + 1) / 2 > t) bi--;
+      while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+      const int bj = t - bi * (bi + 1) / 2;
+      const int i = k + 1 + bi, j = k + 1 + bj;
+      double lik[kTile];
+      const double* lrow = L + (size_t)(i * kTile + lane) * np + k * kTile;
+#pragma unroll
+      for (int c = 0; c < kTile; c++) lik[c] = lrow[c];
+      double* crow = L + (size_t)(i * kTile + lane) * np + j * kTile;
+      const double* ljk = L + (size_t)(j * kTile) * np + k * kTile;
+      for (int c = 0; c < kTile; c++) {       // column c of tile (i,j) uses row c of tile (j,k) (broadcast loads)
+        double s = 0.0;
+        const double* lj = ljk + (size_t)c * np;
+#pragma unroll
+        for (int q = 0; q < kTile; q++) s += lik[q] * lj[q];
+        crow[c] -= s;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (s_fail) {     // reference: solver.info() != Success -> dx = 0
+    if (tid == 0) { hdr[HDR_CHOL_FAIL] = 1; atomicOr(&hdr[HDR_STATUS], ST_CHOL_FAIL); }
+    for (int i = tid; i < n; i += kSolveThreads) dx[i] = 0.f;
+    return;
+  }
+  if (tid == 0) hdr[HDR_CHOL_FAIL] = 0;
+
+  // ---- forward substitution L y = b (tile by tile)
+  for (int k = 0; k < nt; k++) {
+    if (warp == 0) {
+      double yk = y[k * kTile + lane];
+      const double* lrow = L + (size_t)(k * kTile + lane) * np + k * kTile;
+      for (int c = 0; c < kTile; c++) {
+        const double lcc = __shfl_sync(0xffffffffu, lrow[c], c);   // lane c holds L[c][c] when reading its own row
+        double yc = __shfl_sync(0xffffffffu, yk, c) / lcc;
+        if (lane == c) yk = yc;
+        else if (lane > c) yk -= lrow[c] * yc;
+      }
+      y[k * kTile + lane] = yk;
+    }
+    __syncthreads();
+    for (int i = k + 1 + warp; i < nt; i += NW) {
+      const double* lrow = L + (size_t)(i * kTile + lane) * np + k * kTile;
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < kTile; c++) s += lrow[c] * y[k * kTile + c];
+      y[i * kTile + lane] -= s;
+    }
+    __syncthreads();
+  }
+  // ---- backward substitution L^T x = y
+  for (int k = nt - 1; k >= 0; k--) {
+    if (warp == 0) {
+      double xk = y[k * kTile + lane];
+      // column access of the diagonal tile: L[c][lane] for c >= lane
+      for (int c = kTile - 1; c >= 0; c--) {
+        const double lcc = L[(size_t)(k * kTile + c) * np + k * kTile + c];
+        double xc = __shfl_sync(0xffffffffu, xk, c) / lcc;
+        if (lane == c) xk = xc;
+        else if (lane < c) xk -= L[(size_t)(k * kTile + c) * np + k * kTile + lane] * xc;
+      }
+      y[k * kTile + lane] = xk;
+    }
+    __syncthreads();
+    // x_i -= L_ki^T x_k for i < k : lane = column of tile (k,i)
+    for (int i = warp; i < k; i += NW) {
+      double s = 0.0;
+      for (int c = 0; c < kTile; c++) s += L[(size_t)(k * kTile + c) * np + i * kTile + lane] * y[k * kTile + c];
+      y[i * kTile + lane] -= s;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += kSolveThreads) dx[i] = (float)y[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// back substitution + retractions
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void exp_so3(const float* phi, float* q) {
+  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  const float theta_p4 = theta_sq * theta_sq;
+  const float theta = sqrtf(theta_sq);
+  float imag, real;
+  if ((double)theta_sq < 1e-8) {        // double literal comparison in the reference (:128)
+    imag = (float)(0.5 - (1.0 / 48.0) * (double)theta_sq + (1.0 / 3840.0) * (double)theta_p4);
+    real = (float)(1.0 - (1.0 / 8.0) * (double)theta_sq + (1.0 / 384.0) * (double)theta_p4);
+  } else {
+    imag = (float)((double)sinf((float)(0.5 * (double)theta)) / (double)theta);
+    real = cosf((float)(0.5 * (double)theta));
+  }
+  q[0] = imag * phi[0]; q[1] = imag * phi[1]; q[2] = imag * phi[2]; q[3] = real;
+}
+
+__device__ __forceinline__ void cross_inplace(const float* a, float* b) {
+  const float x0 = a[1] * b[2] - a[2] * b[1], x1 = a[2] * b[0] - a[0] * b[2], x2 = a[0] * b[1] - a[1] * b[0];
+  b[0] = x0; b[1] = x1; b[2] = x2;
+}
+
+__device__ __forceinline__ void exp_se3(const float* xi, float* t, float* q) {
+  exp_so3(xi + 3, q);
+  float tau[3] = {xi[0], xi[1], xi[2]};
+  const float phi[3] = {xi[3], xi[4], xi[5]};
+  const float theta_sq = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  const float theta = sqrtf(theta_sq);
+  t[0] = tau[0]; t[1] = tau[1]; t[2] = tau[2];
+  if ((double)theta > 1e-4) {
+    const float a = (1 - cosf(theta)) / theta_sq;
+    cross_inplace(phi, tau);
+    t[0] += a * tau[0]; t[1] += a * tau[1]; t[2] += a * tau[2];
+    const float b = (theta - sinf(theta)) / (theta * theta_sq);
+    cross_inplace(phi, tau);
+    t[0] += b * tau[0]; t[1] += b * tau[1]; t[2] += b * tau[2];
+  }
+}
+
+__global__ void __launch_bounds__(256) ba_backsub_kernel(
+    const int64_t* __restrict__ jj, const int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
+    const int* __restrict__ edgeidx, int HW, int t0, int P,
+    const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
+    const float* __restrict__ dx, float* __restrict__ disps, float* __restrict__ dz_out) {
+  const int m = blockIdx.y;
+  if (m >= hdr[HDR_M]) return;
+  const int ix = kx[m];
+  const int e_begin = rowptr[m], e_end = rowptr[m + 1];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  // dw = sum over rows of frame m of  E[row,:,p] . dx[pose]   with the Q9 guard 0 < pose < P   (reference :1114)
+  float dw = 0.f;
+  {
+    const int ps = ix - t0;
+    if (ps > 0 && ps < P) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; c++) s += __ldg(Eiin + ((size_t)m * 6 + c) * HW + p) * __ldg(dx + ps * 6 + c);
+      dw += s;
+    }
+  }
+  for (int a = e_begin; a < e_end; a++) {
+    const int e = edgeidx[a];
+    const int pj = (int)jj[e] - t0;
+    if (pj > 0 && pj < P) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; c++) s += __ldg(Eij + ((size_t)e * 6 + c) * HW + p) * __ldg(dx + pj * 6 + c);
+      dw += s;
+    }
+  }
+  const float q = 1.0f / __ldg(Cin + (size_t)m * HW + p);
+  const float dz = q * (__ldg(win + (size_t)m * HW + p) - dw);
+  dz_out[(size_t)m * HW + p] = dz;
+  disps[(size_t)ix * HW + p] += dz;       // K8 (:942-955)
+}
+
+__global__ void ba_pose_retr_kernel(float* __restrict__ poses, const float* __restrict__ dx, int t0, int P, float* __restrict__ dx_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P) return;
+  float xi[6], t[3], q[4], dt[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 1}, t1[3], q1[4];
+  float* ps = poses + 7 * (size_t)(t0 + k);
+#pragma unroll
+  for (int c = 0; c < 6; c++) { xi[c] = dx[k * 6 + c]; if (dx_out) dx_out[k * 6 + c] = xi[c]; }
+  t[0] = ps[0]; t[1] = ps[1]; t[2] = ps[2];
+  q[0] = ps[3]; q[1] = ps[4]; q[2] = ps[5]; q[3] = ps[6];
+  exp_se3(xi, dt, dq);
+  q1[0] = dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1];
+  q1[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
+  q1[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
+  q1[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
+  act_so3(dq, t, t1);
+  ps[0] = t1[0] + dt[0]; ps[1] = t1[1] + dt[1]; ps[2] = t1[2] + dt[2];
+  ps[3] = q1[0]; ps[4] = q1[1]; ps[5] = q1[2]; ps[6] = q1[3];
+}
+
+}  // namespace dba
+using namespace dba;
+
+// ---------------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------------
+extern "C" size_t dba_ba_workspace_bytes(int n_frames, int n_edges, int ht, int wd, int t0, int t1) {
+  return make_layout(n_frames, n_edges, ht, wd, t0, t1).total;
+}
+extern "C" size_t dba_ba_system_offset(int n_frames, int n_edges, int ht, int wd, int t0, int t1) {
+  return make_layout(n_frames, n_edges, ht, wd, t0, t1).off_sys;
+}
+extern "C" size_t dba_ba_system_bytes(int t0, int t1) {
+  const size_t n = 6 * (size_t)(t1 - t0 > 0 ? t1 - t0 : 0);
+  return (n * n + n) * sizeof(double);
+}
+
+static int check_ba_args(const dba_ba_args* a, Layout& L) {
+  DBA_CHECK_ARG(a != nullptr, "null args");
+  DBA_CHECK_ARG(a->n_frames > 0 && a->n_edges >= 0 && a->ht > 0 && a->wd > 0, "bad extents");
+  DBA_CHECK_ARG(a->t0 >= 0 && a->t1 >= a->t0 && a->t1 <= a->n_frames, "bad window [t0,t1)");
+  DBA_CHECK_ARG(a->poses && a->disps && a->intrinsics && a->disps_sens, "null state pointer");
+  DBA_CHECK_ARG(a->n_edges == 0 || (a->targets && a->weights && a->ii && a->jj), "null edge pointer");
+  DBA_CHECK_ARG(a->motion_only || (a->eta && a->eta_rows >= 1), "eta missing");
+  DBA_CHECK_ARG(a->workspace != nullptr, "null workspace");
+  DBA_CHECK_ARG(a->n_frames <= 65535, "more than 65535 frames");
+  L = make_layout(a->n_frames, a->n_edges, a->ht, a->wd, a->t0, a->t1);
+  if (a->workspace_bytes < L.total) { dba::set_error("workspace too small: %zu < %zu", a->workspace_bytes, L.total); return DBA_ERR_WORKSPACE; }
+  return DBA_OK;
+}
+
+#define WS(T, off) reinterpret_cast<T*>(reinterpret_cast<char*>(a->workspace) + (off))
+
+extern "C" int dba_ba_prepare(const dba_ba_args* a) {
+  Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  ba_prepare_kernel<<<1, 1024, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, a->t0, a->t1, a->motion_only ? 1 : a->eta_rows,
+                                        WS(int, L.off_hdr), WS(int, L.off_frame2k), WS(int, L.off_kx), WS(int, L.off_rowptr));
+  DBA_CHECK_LAUNCH("ba_prepare");
+  if (a->n_edges > 0) {
+    ba_fill_csr_kernel<<<(a->n_edges + 255) / 256, 256, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, WS(int, L.off_frame2k),
+                                                                  WS(int, L.off_rowptr), WS(int, L.off_edgeidx));
+    DBA_CHECK_LAUNCH("ba_fill_csr");
+  }
+  return DBA_OK;
+}
+
+extern "C" int dba_ba_build(const dba_ba_args* a) {
+  Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const int HW = a->ht * a->wd;
+  DBA_CHECK_CUDA(cudaMemsetAsync(WS(char, L.off_sys), 0, ((size_t)L.n * L.n + L.n) * sizeof(double), st), "ba_build memset");
+  if (L.P == 0) return DBA_OK;
+  double* Hsys = WS(double, L.off_sys);
+  double* bsys = Hsys + (size_t)L.n * L.n;
+  dim3 grid((HW + kChunkPx - 1) / kChunkPx, a->n_frames);   // y: depth frames (CTAs beyond M exit immediately)
+  ba_build_kernel<<<grid, kBuildThreads, 0, st>>>(a->poses, a->disps, a->intrinsics, a->disps_sens, a->targets, a->weights, a->eta,
+                                                  a->eta_rows, a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                  WS(int, L.off_edgeidx), HW, a->wd, a->t0, L.P, a->motion_only, Hsys, bsys,
+                                                  WS(float, L.off_Eij), WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei));
+  DBA_CHECK_LAUNCH("ba_build");
+  if (!a->motion_only) {
+    const int chunks = 2;
+    const int px_per_cta = ((HW + chunks - 1) / chunks + kSchurTP - 1) / kSchurTP * kSchurTP;
+    dim3 g2((HW + px_per_cta - 1) / px_per_cta, a->n_frames);
+    const size_t smem = ((size_t)2 * kSchurTP * (6 * kSchurMaxRows + 2) + 2 * kSchurTP) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "schur smem attr");
+      attr_set = true;
+    }
+    ba_schur_kernel<<<g2, kSchurThreads, smem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                     WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
+                                                     WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+    DBA_CHECK_LAUNCH("ba_schur");
+  }
+  return DBA_OK;
+}
+
+extern "C" int dba_ba_solve(const dba_ba_args* a) {
+  Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
+  if (L.P == 0) return DBA_OK;
+  cudaStream_t st = (cudaStream_t)a->stream;
+  const int HW = a->ht * a->wd;
+  double* Hsys = WS(double, L.off_sys);
+  double* bsys = Hsys + (size_t)L.n * L.n;
+  float* dx = WS(float, L.off_dx);
+  ba_solve_kernel<<<1, kSolveThreads, 0, st>>>(Hsys, bsys, WS(double, L.off_L), L.n, a->lm, a->ep, WS(int, L.off_hdr), dx);
+  DBA_CHECK_LAUNCH("ba_solve");
+  if (!a->motion_only) {
+    DBA_CHECK_ARG(a->dz_out != nullptr, "dz_out missing");
+    dim3 grid((HW + 255) / 256, a->n_frames);
+    ba_backsub_kernel<<<grid, 256, 0, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr), WS(int, L.off_edgeidx),
+                                            HW, a->t0, L.P, WS(float, L.off_Eij), WS(float, L.off_C), WS(float, L.off_w),
+                                            WS(float, L.off_Ei), dx, a->disps, a->dz_out);
+    DBA_CHECK_LAUNCH("ba_backsub");
+  }
+  ba_pose_retr_kernel<<<(L.P + 127) / 128, 128, 0, st>>>(a->poses, dx, a->t0, L.P, a->dx_out);
+  DBA_CHECK_LAUNCH("ba_pose_retr");
+  return DBA_OK;
+}
+
+extern "C" int dba_ba(const dba_ba_args* a, int iterations) {
+  int rc = dba_ba_prepare(a);
+  if (rc) return rc;
+  for (int it = 0; it < iterations; it++) {
+    rc = dba_ba_build(a); if (rc) return rc;
+    rc = dba_ba_solve(a); if (rc) return rc;
+  }
+  return DBA_OK;
+}
+
+extern "C" int dba_ba_read_info(const dba_ba_args* a, int* n_depth_frames, int* device_status) {
+  Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
+  int h[4] = {0, 0, 0, 0};
+  DBA_CHECK_CUDA(cudaMemcpyAsync(h, WS(int, L.off_hdr), sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)a->stream), "read_info copy");
+  DBA_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)a->stream), "read_info sync");
+  if (n_depth_frames) *n_depth_frames = h[HDR_M];
+  if (device_status) *device_status = h[HDR_STATUS];
+  return DBA_OK;
+}

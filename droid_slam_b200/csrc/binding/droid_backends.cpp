@@ -1,0 +1,230 @@
+// `droid_backends` -- drop-in Python extension exporting the reference's nine callables
+// (reference src/droid.cpp:93-259: ba, frame_distance, projmap, depth_filter, iproj, altcorr_forward,
+// altcorr_backward, corr_index_forward, corr_index_backward) with identical positional signatures and return
+// shapes, implemented on the C ABI of include/droid_b200.h (libdroid_b200.so, hand-written sm_100a kernels).
+//
+// torch is used here for what the reference binding uses it for: tensor handles, the caching allocator, the current
+// stream.  Differences from the reference binding, all strictly safer: a CUDAGuard on the tensors' device, launches on
+// torch's CURRENT stream (the reference uses the legacy default stream), dtype/device checks with readable messages.
+// There is no CPU fallback: every call needs CUDA tensors and fails loudly otherwise.
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <vector>
+#include "../../../include/droid_b200.h"
+
+#define CHECK_CONTIGUOUS(x) TORCH_CHECK(x.is_contiguous(), #x " must be contiguous")   // reference src/droid.cpp:89
+#define CHECK_CUDA(x) TORCH_CHECK(x.is_cuda(), #x " must be a CUDA tensor (droid_backends has no CPU path)")
+#define CHECK_F32(x) TORCH_CHECK(x.scalar_type() == torch::kFloat32, #x " must be float32")
+#define CHECK_I64(x) TORCH_CHECK(x.scalar_type() == torch::kInt64, #x " must be int64")
+#define CHECK_INPUT(x) do { CHECK_CONTIGUOUS(x); CHECK_CUDA(x); } while (0)
+
+static inline void check_status(int rc, const char* op) {
+  TORCH_CHECK(rc == DBA_OK, "droid_backends.", op, " failed (status ", rc, "): ", dba_last_error());
+}
+static inline dba_stream_t cur_stream() { return (dba_stream_t)at::cuda::getCurrentCUDAStream().stream(); }
+
+static int dtype_code(const torch::Tensor& t, const char* what) {
+  switch (t.scalar_type()) {
+    case torch::kFloat32: return DBA_F32;
+    case torch::kFloat16: return DBA_F16;
+    case torch::kFloat64: return DBA_F64;
+    case torch::kBFloat16: return DBA_BF16;
+    default: TORCH_CHECK(false, what, ": unsupported dtype ", t.scalar_type());
+  }
+  return -1;
+}
+
+std::vector<torch::Tensor> ba(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor disps_sens,
+                              torch::Tensor targets, torch::Tensor weights, torch::Tensor eta, torch::Tensor ii, torch::Tensor jj,
+                              const int t0, const int t1, const int iterations, const float lm, const float ep,
+                              const bool motion_only) {
+  CHECK_INPUT(targets); CHECK_INPUT(weights); CHECK_INPUT(poses); CHECK_INPUT(disps);
+  CHECK_INPUT(intrinsics); CHECK_INPUT(disps_sens); CHECK_INPUT(ii); CHECK_INPUT(jj);
+  CHECK_F32(targets); CHECK_F32(weights); CHECK_F32(poses); CHECK_F32(disps); CHECK_F32(intrinsics); CHECK_F32(disps_sens);
+  CHECK_I64(ii); CHECK_I64(jj);
+  TORCH_CHECK(poses.dim() == 2 && poses.size(1) == 7, "poses must be [N,7]");
+  TORCH_CHECK(disps.dim() == 3, "disps must be [N,ht,wd]");
+  TORCH_CHECK(disps_sens.sizes() == disps.sizes(), "disps_sens must have the shape of disps");
+  TORCH_CHECK(intrinsics.numel() >= 4, "intrinsics must hold fx,fy,cx,cy");
+  const int N = (int)disps.size(0), ht = (int)disps.size(1), wd = (int)disps.size(2);
+  const int HW = ht * wd;
+  const int E = (int)ii.size(0);
+  TORCH_CHECK(jj.size(0) == E, "ii and jj must have the same length");
+  TORCH_CHECK(targets.numel() == (int64_t)E * 2 * HW && weights.numel() == (int64_t)E * 2 * HW, "targets/weights must be [E,2,ht,wd]");
+  TORCH_CHECK(poses.size(0) >= N || poses.size(0) >= t1, "poses has fewer rows than the optimisation window");
+  TORCH_CHECK(t0 >= 0 && t1 >= t0 && t1 <= N, "invalid window [t0,t1)");
+  if (iterations <= 0) return {torch::Tensor(), torch::Tensor()};   // reference returns two undefined tensors
+  c10::cuda::CUDAGuard guard(poses.device());
+
+  int eta_rows = 1;
+  torch::Tensor eta_c = eta;
+  if (!motion_only) {
+    CHECK_CUDA(eta); CHECK_F32(eta);
+    eta_c = eta.contiguous();   // the reference only needs it .view()-able
+    TORCH_CHECK(eta_c.numel() % HW == 0 && eta_c.numel() > 0, "eta must be [M,ht,wd]");
+    eta_rows = (int)(eta_c.numel() / HW);
+  }
+  const int n_frames = std::min<int>(N, (int)poses.size(0));
+  const size_t ws_bytes = dba_ba_workspace_bytes(n_frames, E, ht, wd, t0, t1);
+  auto ws = torch::empty({(int64_t)ws_bytes}, torch::TensorOptions().dtype(torch::kUInt8).device(poses.device()));
+  const int P = t1 - t0;
+  auto dx = torch::empty({P, 6}, poses.options());
+
+  dba_ba_args a;
+  a.poses = poses.data_ptr<float>(); a.disps = disps.data_ptr<float>(); a.intrinsics = intrinsics.data_ptr<float>();
+  a.disps_sens = disps_sens.data_ptr<float>(); a.targets = targets.data_ptr<float>(); a.weights = weights.data_ptr<float>();
+  a.eta = motion_only ? nullptr : eta_c.data_ptr<float>(); a.eta_rows = eta_rows;
+  a.ii = ii.data_ptr<int64_t>(); a.jj = jj.data_ptr<int64_t>();
+  a.n_frames = n_frames; a.n_edges = E; a.ht = ht; a.wd = wd; a.t0 = t0; a.t1 = t1;
+  a.lm = lm; a.ep = ep; a.motion_only = motion_only ? 1 : 0;
+  a.dx_out = dx.data_ptr<float>(); a.dz_out = nullptr;
+  a.workspace = ws.data_ptr(); a.workspace_bytes = ws_bytes; a.stream = cur_stream();
+
+  torch::Tensor dz;
+  if (!motion_only) {
+    int M = eta_rows;
+    if (eta_rows == 1) {   // broadcast eta: the number of depth frames has to come from the device (one sync)
+      check_status(dba_ba_prepare(&a), "ba");
+      int st = 0;
+      check_status(dba_ba_read_info(&a, &M, &st), "ba");
+    }
+    dz = torch::empty({M, HW}, poses.options());
+    a.dz_out = dz.data_ptr<float>();
+  }
+  check_status(dba_ba(&a, iterations), "ba");
+  return {dx, dz};
+}
+
+torch::Tensor frame_distance(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor ii, torch::Tensor jj,
+                             const float beta) {
+  CHECK_INPUT(poses); CHECK_INPUT(disps); CHECK_INPUT(intrinsics); CHECK_INPUT(ii); CHECK_INPUT(jj);
+  CHECK_F32(poses); CHECK_F32(disps); CHECK_F32(intrinsics); CHECK_I64(ii); CHECK_I64(jj);
+  TORCH_CHECK(disps.dim() == 3, "disps must be [N,ht,wd]");
+  c10::cuda::CUDAGuard guard(poses.device());
+  const int num = (int)ii.size(0);
+  auto dist = torch::empty({num}, poses.options());
+  check_status(dba_frame_distance(poses.data_ptr<float>(), disps.data_ptr<float>(), intrinsics.data_ptr<float>(), ii.data_ptr<int64_t>(),
+                                  jj.data_ptr<int64_t>(), dist.data_ptr<float>(), num, (int)disps.size(1), (int)disps.size(2), beta,
+                                  cur_stream()), "frame_distance");
+  return dist;
+}
+
+std::vector<torch::Tensor> projmap(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor ii, torch::Tensor jj) {
+  CHECK_INPUT(poses); CHECK_INPUT(disps); CHECK_INPUT(intrinsics); CHECK_INPUT(ii); CHECK_INPUT(jj);
+  CHECK_F32(poses); CHECK_F32(disps); CHECK_F32(intrinsics); CHECK_I64(ii); CHECK_I64(jj);
+  TORCH_CHECK(disps.dim() == 3, "disps must be [N,ht,wd]");
+  c10::cuda::CUDAGuard guard(poses.device());
+  const int num = (int)ii.size(0), ht = (int)disps.size(1), wd = (int)disps.size(2);
+  auto coords = torch::empty({num, ht, wd, 3}, poses.options());
+  auto valid = torch::empty({num, ht, wd, 1}, poses.options());
+  check_status(dba_projmap(poses.data_ptr<float>(), disps.data_ptr<float>(), intrinsics.data_ptr<float>(), ii.data_ptr<int64_t>(),
+                           jj.data_ptr<int64_t>(), coords.data_ptr<float>(), valid.data_ptr<float>(), num, ht, wd, cur_stream()), "projmap");
+  return {coords, valid};
+}
+
+torch::Tensor iproj(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics) {
+  CHECK_INPUT(poses); CHECK_INPUT(disps); CHECK_INPUT(intrinsics);
+  CHECK_F32(poses); CHECK_F32(disps); CHECK_F32(intrinsics);
+  TORCH_CHECK(disps.dim() == 3, "disps must be [N,ht,wd]");
+  TORCH_CHECK(poses.size(0) >= disps.size(0), "need one pose per disparity map");
+  c10::cuda::CUDAGuard guard(poses.device());
+  const int nm = (int)disps.size(0), ht = (int)disps.size(1), wd = (int)disps.size(2);
+  auto points = torch::empty({nm, ht, wd, 3}, disps.options());
+  check_status(dba_iproj(poses.data_ptr<float>(), disps.data_ptr<float>(), intrinsics.data_ptr<float>(), points.data_ptr<float>(), nm, ht,
+                         wd, cur_stream()), "iproj");
+  return points;
+}
+
+torch::Tensor depth_filter(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor ix, torch::Tensor thresh) {
+  CHECK_INPUT(poses); CHECK_INPUT(disps); CHECK_INPUT(intrinsics); CHECK_INPUT(ix); CHECK_INPUT(thresh);
+  CHECK_F32(poses); CHECK_F32(disps); CHECK_F32(intrinsics); CHECK_I64(ix); CHECK_F32(thresh);
+  TORCH_CHECK(disps.dim() == 3, "disps must be [N,ht,wd]");
+  c10::cuda::CUDAGuard guard(poses.device());
+  const int num = (int)ix.size(0), ht = (int)disps.size(1), wd = (int)disps.size(2);
+  auto counter = torch::empty({num, ht, wd}, disps.options());
+  check_status(dba_depth_filter(poses.data_ptr<float>(), disps.data_ptr<float>(), intrinsics.data_ptr<float>(), ix.data_ptr<int64_t>(),
+                                thresh.data_ptr<float>(), counter.data_ptr<float>(), num, (int)disps.size(0), ht, wd, cur_stream()),
+               "depth_filter");
+  return counter;
+}
+
+std::vector<torch::Tensor> corr_index_forward(torch::Tensor volume, torch::Tensor coords, int radius) {
+  CHECK_INPUT(volume); CHECK_INPUT(coords); CHECK_F32(coords);
+  TORCH_CHECK(volume.dim() == 5 && coords.dim() == 4 && coords.size(1) == 2, "volume [N,h1,w1,h2,w2], coords [N,2,h1,w1]");
+  TORCH_CHECK(coords.size(0) == volume.size(0) && coords.size(2) == volume.size(1) && coords.size(3) == volume.size(2), "coords/volume mismatch");
+  c10::cuda::CUDAGuard guard(volume.device());
+  const int n = (int)volume.size(0), h1 = (int)volume.size(1), w1 = (int)volume.size(2), h2 = (int)volume.size(3), w2 = (int)volume.size(4);
+  auto corr = torch::empty({n, 2 * radius + 1, 2 * radius + 1, h1, w1}, volume.options());
+  check_status(dba_corr_index_forward(volume.data_ptr(), coords.data_ptr<float>(), corr.data_ptr(), n, h1, w1, h2, w2, radius,
+                                      dtype_code(volume, "corr_index_forward"), cur_stream()), "corr_index_forward");
+  return {corr};
+}
+
+std::vector<torch::Tensor> corr_index_backward(torch::Tensor volume, torch::Tensor coords, torch::Tensor corr_grad, int radius) {
+  CHECK_INPUT(volume); CHECK_INPUT(coords); CHECK_INPUT(corr_grad); CHECK_F32(coords);
+  TORCH_CHECK(volume.dim() == 5 && coords.dim() == 4, "volume [N,h1,w1,h2,w2], coords [N,2,h1,w1]");
+  TORCH_CHECK(corr_grad.scalar_type() == volume.scalar_type(), "corr_grad must have the dtype of volume");
+  c10::cuda::CUDAGuard guard(volume.device());
+  const int n = (int)volume.size(0), h1 = (int)volume.size(1), w1 = (int)volume.size(2), h2 = (int)volume.size(3), w2 = (int)volume.size(4);
+  auto volume_grad = torch::empty_like(volume);
+  check_status(dba_corr_index_backward(coords.data_ptr<float>(), corr_grad.data_ptr(), volume_grad.data_ptr(), n, h1, w1, h2, w2, radius,
+                                       dtype_code(volume, "corr_index_backward"), cur_stream()), "corr_index_backward");
+  return {volume_grad};
+}
+
+std::vector<torch::Tensor> altcorr_forward(torch::Tensor fmap1, torch::Tensor fmap2, torch::Tensor coords, torch::Tensor ii,
+                                           torch::Tensor jj, int radius) {
+  CHECK_INPUT(fmap1); CHECK_INPUT(fmap2); CHECK_INPUT(coords); CHECK_F32(coords);
+  CHECK_CUDA(ii); CHECK_CUDA(jj); CHECK_I64(ii); CHECK_I64(jj);
+  TORCH_CHECK(fmap1.dim() == 5 && fmap2.dim() == 5 && coords.dim() == 5 && coords.size(2) == 2, "fmaps [B,N,C,H,W], coords [B,M,2,H,W]");
+  TORCH_CHECK(fmap1.scalar_type() == fmap2.scalar_type(), "fmap1/fmap2 dtype mismatch");
+  c10::cuda::CUDAGuard guard(fmap1.device());
+  auto iic = ii.contiguous(), jjc = jj.contiguous();
+  const int B = (int)coords.size(0), M = (int)coords.size(1), H = (int)coords.size(3), W = (int)coords.size(4);
+  TORCH_CHECK(iic.size(0) == M && jjc.size(0) == M, "ii/jj must have one entry per edge");
+  TORCH_CHECK(fmap1.size(3) == H && fmap1.size(4) == W, "fmap1 spatial size must match coords");
+  const int D = 2 * radius + 1;
+  auto out = torch::empty({B, M, D, D, H, W}, fmap1.options());
+  check_status(dba_altcorr_forward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr<float>(), iic.data_ptr<int64_t>(),
+                                   jjc.data_ptr<int64_t>(), out.data_ptr(), B, (int)fmap1.size(1), (int)fmap2.size(1), (int)fmap1.size(2), H, W,
+                                   (int)fmap2.size(3), (int)fmap2.size(4), M, radius, dtype_code(fmap1, "altcorr_forward"), cur_stream()),
+               "altcorr_forward");
+  return {out.permute({0, 1, 3, 2, 4, 5})};   // reference src/altcorr_kernel.cu:171
+}
+
+std::vector<torch::Tensor> altcorr_backward(torch::Tensor fmap1, torch::Tensor fmap2, torch::Tensor coords, torch::Tensor corr_grad,
+                                            torch::Tensor ii, torch::Tensor jj, int radius) {
+  // corr_grad is the gradient of the tensor altcorr_forward returned ([B,M,x-off,y-off,H,W]); the reference
+  // (src/droid.cpp:212-226 -> src/altcorr_kernel.cu:175-225) un-permutes it and spreads it over the raw window.
+  CHECK_INPUT(fmap1); CHECK_INPUT(fmap2); CHECK_INPUT(coords); CHECK_INPUT(corr_grad); CHECK_F32(coords);
+  CHECK_CUDA(ii); CHECK_CUDA(jj); CHECK_I64(ii); CHECK_I64(jj);
+  c10::cuda::CUDAGuard guard(fmap1.device());
+  auto iic = ii.contiguous(), jjc = jj.contiguous();
+  auto cg = corr_grad.to(torch::kFloat32).contiguous();   // kernel reads a float accessor (src/altcorr_kernel.cu:84)
+  const int B = (int)coords.size(0), M = (int)coords.size(1), H = (int)coords.size(3), W = (int)coords.size(4);
+  const int D = 2 * radius + 1;
+  TORCH_CHECK(cg.numel() == (int64_t)B * M * D * D * H * W, "corr_grad must be [B,M,2r+1,2r+1,H,W]");
+  auto g1 = torch::empty_like(fmap1), g2 = torch::empty_like(fmap2);
+  check_status(dba_altcorr_backward(fmap1.data_ptr(), fmap2.data_ptr(), coords.data_ptr<float>(), cg.data_ptr<float>(), iic.data_ptr<int64_t>(),
+                                    jjc.data_ptr<int64_t>(), g1.data_ptr(), g2.data_ptr(), B, (int)fmap1.size(1), (int)fmap2.size(1),
+                                    (int)fmap1.size(2), H, W, (int)fmap2.size(3), (int)fmap2.size(4), M, radius,
+                                    dtype_code(fmap1, "altcorr_backward"), cur_stream()), "altcorr_backward");
+  return {g1, g2};
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "B200-native droid_backends (drop-in for princeton-vl/DROID-SLAM src/droid.cpp)";
+  // bundle adjustment kernels
+  m.def("ba", &ba, "bundle adjustment");
+  m.def("frame_distance", &frame_distance, "frame_distance");
+  m.def("projmap", &projmap, "projmap");
+  m.def("depth_filter", &depth_filter, "depth_filter");
+  m.def("iproj", &iproj, "back projection");
+  // correlation volume kernels
+  m.def("altcorr_forward", &altcorr_forward, "ALTCORR forward");
+  m.def("altcorr_backward", &altcorr_backward, "ALTCORR backward");
+  m.def("corr_index_forward", &corr_index_forward, "INDEX forward");
+  m.def("corr_index_backward", &corr_index_backward, "INDEX backward");
+  m.def("_b200_native", []() { return true; });
+}

@@ -53,8 +53,8 @@ int dba_corr_index_backward(const float* coords, const void* corr_grad, void* vo
  * fmap1 [B,N1,C,H,W], fmap2 [B,N2,C,H2,W2], coords [B,M,2,H,W] f32, ii,jj [M] int64 (frame indices into
  * fmap1 / fmap2).  forward writes `out` as a CONTIGUOUS [B,M,2r+1(y-off),2r+1(x-off),H,W] tensor; the binding
  * returns its permute(0,1,3,2,4,5) view like the reference (:171).
- * backward consumes corr_grad [B,M,2r+2,2r+2,H,W] f32 (raw-window gradient, what the reference kernel reads)
- * and fully overwrites fmap1_grad / fmap2_grad. */
+ * backward consumes corr_grad [B,M,2r+1(x-off),2r+1(y-off),H,W] f32 -- the gradient of the returned (permuted)
+ * tensor, as the reference host function does (:175-207) -- and fully overwrites fmap1_grad / fmap2_grad. */
 int dba_altcorr_forward(const void* fmap1, const void* fmap2, const float* coords,
                         const int64_t* ii, const int64_t* jj, void* out,
                         int B, int N1, int N2, int C, int H, int W, int H2, int W2, int M,

@@ -139,34 +139,46 @@ def altcorr_forward(fmap1, fmap2, coords, ii, jj, radius):
 
 
 def altcorr_backward(fmap1, fmap2, coords, corr_grad, ii, jj, radius):
-    """src/altcorr_kernel.cu:78-129,175-225.  corr_grad here is the gradient w.r.t. the RAW (2r+2)^2 window
-    [B,M,D,D,H,W] (that is what the kernel consumes; the Python wrapper that feeds it is broken).
-    Note the kernel multiplies by the un-scaled features (no /4)."""
+    """src/altcorr_kernel.cu:78-129 (kernel) and :175-225 (host).  corr_grad [B,M,2r+1(x),2r+1(y),H,W] float32 is the
+    gradient of the tensor altcorr_forward returned; the host un-permutes it, spreads it over the raw (2r+2)^2 window
+    with the bilinear weights (g1+g2+g3+g4, fp32) and the kernel scatters g*fmap (un-scaled features, no /4;
+    g and the products rounded in the feature dtype; atomics -> order not defined, compared with a tolerance)."""
     r = radius
     D = 2 * r + 2
     B, M, _, H, W = coords.shape
     C = fmap1.shape[2]
     H2, W2 = fmap2.shape[3], fmap2.shape[4]
     dt = fmap1.dtype
-    g1 = torch.zeros_like(fmap1, dtype=torch.float64)
-    g2 = torch.zeros_like(fmap2, dtype=torch.float64)
+    grad = corr_grad.float().permute(0, 1, 3, 2, 4, 5)           # [B,M,a(y),c(x),H,W]   (:190)
+    x = coords[:, :, 0, None, None]; y = coords[:, :, 1, None, None]
+    dx = x - torch.floor(x); dy = y - torch.floor(y)
+    g1 = torch.zeros(B, M, D, D, H, W); g2 = torch.zeros_like(g1); g3 = torch.zeros_like(g1); g4 = torch.zeros_like(g1)
+    g1[:, :, 0:D - 1, 0:D - 1] = (1 - dx) * (1 - dy) * grad
+    g2[:, :, 0:D - 1, 1:D] = (dx) * (1 - dy) * grad
+    g3[:, :, 1:D, 0:D - 1] = (1 - dx) * (dy) * grad
+    g4[:, :, 1:D, 1:D] = (dx) * (dy) * grad
+    raw = g1 + g2 + g3 + g4                                        # (:203)
+    g1o = torch.zeros_like(fmap1, dtype=torch.float64)
+    g2o = torch.zeros_like(fmap2, dtype=torch.float64)
     big = 1 << 20
     fxi = torch.nan_to_num(torch.floor(coords[:, :, 0]), nan=0.0, posinf=big, neginf=-big).clamp(-big, big).long()
     fyi = torch.nan_to_num(torch.floor(coords[:, :, 1]), nan=0.0, posinf=big, neginf=-big).clamp(-big, big).long()
     for m in range(M):
         ix = int(ii[m]); jx = int(jj[m])
-        f1 = fmap1[:, ix].double()                              # [B,C,H,W]
-        f2 = fmap2[:, jx].double().reshape(B, C, H2 * W2)
+        f1 = fmap1[:, ix].reshape(B, C, H * W)
+        f2 = fmap2[:, jx].reshape(B, C, H2 * W2)
         for a in range(D):
             for c in range(D):
                 i1 = fyi[:, m] + (a - r); j1 = fxi[:, m] + (c - r)
-                inb = ((i1 >= 0) & (i1 < H2) & (j1 >= 0) & (j1 < W2))
+                inb = ((i1 >= 0) & (i1 < H2) & (j1 >= 0) & (j1 < W2)).reshape(B, 1, H * W)
                 lin = (i1.clamp(0, H2 - 1) * W2 + j1.clamp(0, W2 - 1)).reshape(B, 1, H * W)
-                g = (corr_grad[:, m, a, c].to(dt).double() * inb).reshape(B, 1, H * W)     # scalar_t g (:113)
+                g = raw[:, m, a, c].to(dt).reshape(B, 1, H * W)                               # scalar_t g (:113)
                 f2g = torch.gather(f2, 2, lin.expand(B, C, H * W))
-                g1[:, ix] += (g * f2g).reshape(B, C, H, W)
-                g2[:, jx].reshape(B, C, H2 * W2).scatter_add_(2, lin.expand(B, C, H * W), g * f1.reshape(B, C, H * W))
-    return [g1.to(dt), g2.to(dt)]
+                t1 = torch.where(inb, (g * f2g), torch.zeros((), dtype=dt)).double()           # product in scalar_t
+                t2 = torch.where(inb, (g * f1), torch.zeros((), dtype=dt)).double()
+                g1o[:, ix] += t1.reshape(B, C, H, W)
+                g2o[:, jx].reshape(B, C, H2 * W2).scatter_add_(2, lin.expand(B, C, H * W), t2)
+    return [g1o.to(dt), g2o.to(dt)]
 
 
 # ---- Python-side construction (modules/corr.py) -----------------------------------------------

@@ -1,0 +1,243 @@
+"""GPU parity tests: the hand-written sm_100a kernels, called through the C ABI (ctypes) and through the
+`droid_backends` pybind surface, against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 outputs within 1e-4 relative (with an absolute floor of 1e-4*scale),
+index/count outputs bit-exact.  corr_index f16/f32 are expected bit-identical to the oracle's restatement of the
+reference rounding order; the tests assert >= 99.9 % identical elements and the tolerance for the rest.
+"""
+import ctypes
+
+import pytest
+import torch
+
+import oracle
+from droid_slam_b200 import c_api, synth
+from util import (DT, c_ba, c_corr_index_backward, c_corr_index_forward, frac_equal, ptr, rel_err, stream)
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _corr_case(n, h1, w1, h2, w2, dtype, seed, spread=1.0):
+    g = torch.Generator().manual_seed(seed)
+    vol = torch.randn(n, h1, w1, h2, w2, generator=g).to(dtype)
+    cx = torch.rand(n, 1, h1, w1, generator=g) * (w2 + 8 * spread) - 4 * spread
+    cy = torch.rand(n, 1, h1, w1, generator=g) * (h2 + 8 * spread) - 4 * spread
+    return vol, torch.cat([cx, cy], 1).contiguous()
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 6, 8, 6, 8), (3, 5, 7, 12, 16), (2, 4, 6, 24, 32), (1, 3, 5, 9, 11), (2, 2, 3, 6, 12)])
+def test_corr_index_forward_matches_oracle(capi, dtype, shape):
+    vol, coords = _corr_case(*shape, dtype, seed=sum(shape))
+    # a few special coordinates: integers, far outside, exactly on the border
+    coords[0, :, 0, 0] = torch.tensor([3.0, 2.0]); coords[0, :, 0, 1] = torch.tensor([-100.0, 5.0])
+    coords[0, :, 1, 0] = torch.tensor([1e9, -1e9]); coords[0, :, 1, 1] = torch.tensor([-0.5, shape[3] - 0.5])
+    got = c_corr_index_forward(capi, vol.to(dev), coords.to(dev), 3)
+    if dtype == torch.bfloat16:      # not dispatched by the reference: oracle = fp32 math on bf16-rounded inputs
+        ref, = oracle.corr_index_forward(vol.float(), coords, 3)
+        assert rel_err(got.float(), ref, floor=1.0) < 1e-2
+        return
+    ref, = oracle.corr_index_forward(vol, coords, 3)
+    assert torch.isfinite(got.float()).all()
+    assert frac_equal(got, ref) >= 0.999
+    tol = {torch.float16: 2e-3, torch.float32: 1e-6, torch.float64: 1e-12}[dtype]
+    assert rel_err(got, ref, floor=1.0) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("radius", [0, 1, 2, 4])
+def test_corr_index_forward_other_radii(capi, dtype, radius):
+    vol, coords = _corr_case(2, 4, 5, 8, 8, dtype, seed=radius)
+    got = c_corr_index_forward(capi, vol.to(dev), coords.to(dev), radius)
+    ref, = oracle.corr_index_forward(vol, coords, radius)
+    assert frac_equal(got, ref) >= 0.999 and rel_err(got, ref) < 2e-3
+
+
+def test_corr_index_forward_nonfinite_coords(capi):
+    vol, coords = _corr_case(1, 4, 8, 8, 8, torch.float32, seed=11)
+    coords[0, 0, 0, 0] = float("inf"); coords[0, 1, 0, 1] = float("-inf")
+    got = c_corr_index_forward(capi, vol.to(dev), coords.to(dev), 3).cpu()
+    assert (got[0, :, :, 0, 0] == 0).all() and (got[0, :, :, 0, 1] == 0).all()     # nothing in bounds -> zeros, like the reference
+    ref, = oracle.corr_index_forward(vol, coords, 3)
+    assert torch.equal(got[0, :, :, 1:], ref[0, :, :, 1:])
+
+
+def test_corr_index_forward_empty_and_unaligned(capi, backends):
+    e = backends.corr_index_forward(torch.zeros(0, 4, 4, 4, 8, device=dev), torch.zeros(0, 2, 4, 4, device=dev), 3)[0]
+    assert e.shape == (0, 7, 7, 4, 4)
+    # a volume view whose base pointer is not 16-byte aligned must take the generic path and still be right
+    vol, coords = _corr_case(2, 4, 4, 8, 8, torch.float16, seed=5)
+    buf = torch.zeros(vol.numel() + 1, dtype=torch.float16, device=dev)
+    v = buf[1:].view(vol.shape); v.copy_(vol)
+    got = backends.corr_index_forward(v, coords.to(dev), 3)[0]
+    ref, = oracle.corr_index_forward(vol, coords, 3)
+    assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+def test_corr_index_backward_matches_oracle(capi, dtype):
+    vol, coords = _corr_case(2, 5, 6, 12, 16, dtype, seed=7)
+    g = torch.Generator().manual_seed(8)
+    grad = torch.randn(2, 7, 7, 5, 6, generator=g).to(dtype)
+    got = c_corr_index_backward(capi, vol.to(dev), coords.to(dev), grad.to(dev), 3)
+    ref, = oracle.corr_index_backward(vol, coords, grad, 3)
+    assert frac_equal(got, ref) >= 0.999
+    assert rel_err(got, ref) < {torch.float16: 4e-3, torch.float32: 1e-6, torch.float64: 1e-12}[dtype]
+
+
+def test_corr_pyramid_lookup_like_corrblock(backends):
+    """CorrBlock.__call__ call pattern (reference modules/corr.py:40-50) on fp16 volumes, 4 levels."""
+    s = synth.make_scene(dict(E=6, N=4, ht=16, wd=24, stereo=False, itrs=1, lm=1e-4, ep=0.1), seed=4)
+    pyr, coords, _ = synth.make_corr_inputs(s, dtype=torch.float16, channels=16, levels=3)
+    outs = []
+    for i, vol in enumerate(pyr):
+        c, = backends.corr_index_forward(vol.to(dev), (coords / 2 ** i).to(dev), 3)
+        outs.append(c.view(1, 6, -1, 16, 24))
+    got = torch.cat(outs, dim=2).cpu()
+    ref = oracle.corr_block_lookup(pyr, coords.permute(0, 2, 3, 1)[None], 3)
+    assert got.shape == ref.shape == (1, 6, 3 * 49, 16, 24)
+    assert frac_equal(got, ref) >= 0.999
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+def test_altcorr_forward_matches_oracle(backends, dtype):
+    g = torch.Generator().manual_seed(21)
+    B, N, C, H, W = 1, 4, 32, 12, 16
+    fmaps = torch.randn(B, N, C, H, W, generator=g).to(dtype)
+    pyr = oracle.fmap_pyramid(fmaps, 3)
+    ii = torch.tensor([0, 1, 2, 3, 0]); jj = torch.tensor([1, 2, 3, 3, 3])
+    coords = torch.rand(B, 5, 2, H, W, generator=g) * torch.tensor([W + 6.0, H + 6.0]).view(1, 1, 2, 1, 1) - 3
+    for lvl in range(3):
+        c = (coords / 2 ** lvl).contiguous()
+        got, = backends.altcorr_forward(pyr[0].to(dev), pyr[lvl].contiguous().to(dev), c.to(dev), ii.to(dev), jj.to(dev), 3)
+        ref, = oracle.altcorr_forward(pyr[0], pyr[lvl], c, ii, jj, 3)
+        assert got.shape == ref.shape and got.stride() == ref.stride()      # same permuted view as the reference (:171)
+        tol = {torch.float16: 2e-2, torch.float32: 1e-4, torch.float64: 1e-6}[dtype]   # channel summation order differs
+        assert rel_err(got, ref, floor=1.0) < tol
+
+
+def test_altcorr_backward_matches_oracle(backends):
+    g = torch.Generator().manual_seed(22)
+    B, N, C, H, W = 1, 3, 8, 6, 8
+    f1 = torch.randn(B, N, C, H, W, generator=g); f2 = torch.randn(B, N, C, H, W, generator=g)
+    ii = torch.tensor([0, 1, 2]); jj = torch.tensor([1, 2, 2])
+    coords = torch.rand(B, 3, 2, H, W, generator=g) * 8 - 1
+    grad = torch.randn(B, 3, 7, 7, H, W, generator=g)
+    g1, g2 = backends.altcorr_backward(f1.to(dev), f2.to(dev), coords.to(dev), grad.to(dev), ii.to(dev), jj.to(dev), 3)
+    r1, r2 = oracle.altcorr_backward(f1, f2, coords, grad, ii, jj, 3)
+    assert rel_err(g1, r1) < 1e-4 and rel_err(g2, r2) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+def _scene(E=40, N=10, ht=24, wd=32, stereo=False, seed=0, **kw):
+    return synth.make_scene(dict(E=E, N=N, ht=ht, wd=wd, stereo=stereo, itrs=2, lm=1e-4, ep=0.1), seed=seed, **kw)
+
+
+def test_projmap_iproj_frame_distance_depth_filter(backends):
+    s = _scene(seed=3)
+    P, D, K = s["poses"], s["disps"], s["intrinsics"]
+    ii, jj = s["ii"], s["jj"]
+    c, v = backends.projmap(P.to(dev), D.to(dev), K.to(dev), ii.to(dev), jj.to(dev))
+    rc, rv = oracle.projmap(P, D, K, ii, jj)
+    assert c.shape == (40, 24, 32, 3) and v.shape == (40, 24, 32, 1)
+    assert rel_err(c, rc, floor=1.0) < 1e-4 and frac_equal(v, rv) > 0.9999
+    pts = backends.iproj(P.to(dev), D.to(dev), K.to(dev))
+    assert rel_err(pts, oracle.iproj(P, D, K), floor=1.0) < 1e-4
+    fd = backends.frame_distance(P.to(dev), D.to(dev), K.to(dev), ii.to(dev), jj.to(dev), 0.3)
+    assert rel_err(fd, oracle.frame_distance(P, D, K, ii, jj, 0.3), floor=1.0) < 1e-4
+    # DepthVideo.distance pattern (reference depth_video.py:181-211): bidirectional, all pairs
+    n = 6
+    a, b = torch.meshgrid(torch.arange(n), torch.arange(n), indexing="ij")
+    a = a.reshape(-1); b = b.reshape(-1)
+    d1 = backends.frame_distance(P[:n].clone().to(dev), D.to(dev), K.to(dev), a.to(dev), b.to(dev), 0.3)
+    d2 = backends.frame_distance(P[:n].clone().to(dev), D.to(dev), K.to(dev), b.to(dev), a.to(dev), 0.3)
+    ref = .5 * (oracle.frame_distance(P, D, K, a, b, 0.3) + oracle.frame_distance(P, D, K, b, a, 0.3))
+    assert rel_err(.5 * (d1 + d2), ref, floor=1.0) < 1e-4
+    ix = torch.arange(10)
+    th = torch.full((10,), 0.05)
+    cnt = backends.depth_filter(P.to(dev), D.to(dev), K.to(dev), ix.to(dev), th.to(dev))
+    rcnt = oracle.depth_filter(P, D, K, ix, th)
+    assert cnt.shape == rcnt.shape
+    assert frac_equal(cnt, rcnt) > 0.999            # integer counts; a threshold flip needs |err - t| < 1e-7
+    assert float(rcnt.max()) >= 1
+
+
+def test_frame_distance_invalid_pairs_return_1000(backends):
+    s = _scene(seed=4)
+    P = s["poses"].clone(); P[5, 2] = -50.0          # frame 5 far behind: almost nothing valid
+    fd = backends.frame_distance(P.to(dev), s["disps"].to(dev), s["intrinsics"].to(dev), torch.tensor([0], device=dev), torch.tensor([5], device=dev), 0.3)
+    ref = oracle.frame_distance(P, s["disps"], s["intrinsics"], torch.tensor([0]), torch.tensor([5]), 0.3)
+    assert float(ref) == 1000.0 and float(fd) == 1000.0
+
+
+# ---------------------------------------------------------------------------------------------------
+def _run_ba(capi, s, itrs, motion_only=False, lm=None, ep=None):
+    lm = s["lm"] if lm is None else lm; ep = s["ep"] if ep is None else ep
+    P, D = s["poses"].to(dev), s["disps"].to(dev)
+    dx, dz, M, st, _ = c_ba(capi, P, D, s["intrinsics"].to(dev), s["disps_sens"].to(dev), s["targets"].to(dev), s["weights"].to(dev),
+                            s["eta"].to(dev), s["ii"].to(dev), s["jj"].to(dev), s["t0"], s["t1"], itrs, lm, ep, motion_only, s["M"])
+    P64, D64 = s["poses"].double(), s["disps"].double()
+    (rdx, rdz), ok = oracle.ba(P64, D64, s["intrinsics"], s["disps_sens"], s["targets"], s["weights"], s["eta"], s["ii"], s["jj"],
+                               s["t0"], s["t1"], itrs, lm, ep, motion_only, dtype=torch.float64, return_info=True)
+    return dict(P=P.cpu(), D=D.cpu(), dx=dx.cpu(), dz=dz.cpu(), M=M, st=st, P64=P64, D64=D64, rdx=rdx, rdz=rdz, ok=ok)
+
+
+@pytest.mark.parametrize("cfg", [dict(E=24, N=8, ht=48, wd=64), dict(E=40, N=10, ht=24, wd=32), dict(E=60, N=12, ht=20, wd=28, rgbd=True),
+                                 dict(E=30, N=9, ht=16, wd=24, stereo=True)])
+@pytest.mark.parametrize("itrs", [1, 3])
+def test_ba_matches_fp64_oracle(capi, cfg, itrs):
+    rgbd = cfg.pop("rgbd", False) if "rgbd" in cfg else False
+    cfg = dict(cfg)
+    s = _scene(seed=itrs, rgbd=rgbd, **cfg)
+    r = _run_ba(capi, s, itrs)
+    assert r["M"] == s["M"] and r["st"] == 0 and r["ok"]
+    assert rel_err(r["P"], r["P64"], floor=1.0) < 1e-4            # updated poses
+    assert rel_err(r["D"], r["D64"], floor=1.0) < 1e-4            # updated inverse depths
+    assert rel_err(r["dx"], r["rdx"], floor=1e-2) < 1e-3          # last step itself (small numbers: looser relative floor)
+    assert rel_err(r["dz"], r["rdz"], floor=1.0) < 1e-4
+
+
+def test_ba_motion_only(capi):
+    s = _scene(seed=9)
+    r = _run_ba(capi, s, 2, motion_only=True)
+    assert r["st"] == 0
+    assert rel_err(r["P"], r["P64"], floor=1.0) < 1e-4
+    assert torch.equal(r["D"], s["disps"])                        # depths untouched
+    assert torch.isnan(r["dz"]).all()                             # dz_out untouched when motion_only
+
+
+def test_ba_backend_settings_and_fixed_window(capi):
+    """global-BA settings of update_lowmem (lm=1e-5, ep=1e-2, reference factor_graph.py:327-328) and a window whose
+    first frames are fixed (t0 > 1) with edges reaching into the fixed part."""
+    s = _scene(E=60, N=14, ht=16, wd=24, seed=10)
+    s["t0"] = 4
+    kx = torch.unique(torch.cat([torch.arange(s["t0"], s["t1"]), s["ii"]])); s["M"] = kx.shape[0]
+    r = _run_ba(capi, s, 2, lm=1e-5, ep=1e-2)
+    assert r["st"] == 0 and r["M"] == s["M"]
+    assert rel_err(r["P"], r["P64"], floor=1.0) < 1e-4 and rel_err(r["D"], r["D64"], floor=1.0) < 1e-4
+    assert torch.equal(r["P"][:4], s["poses"][:4])                # poses before t0 are not touched
+
+
+def test_ba_pybind_matches_capi_and_mutates_in_place(capi, backends):
+    s = _scene(seed=12)
+    r = _run_ba(capi, s, 2)
+    P, D = s["poses"].to(dev), s["disps"].to(dev)
+    out = backends.ba(P, D, s["intrinsics"].to(dev), s["disps_sens"].to(dev), s["targets"].to(dev), s["weights"].to(dev),
+                      s["eta"].to(dev), s["ii"].to(dev), s["jj"].to(dev), s["t0"], s["t1"], 2, s["lm"], s["ep"], False)
+    assert len(out) == 2 and out[0].shape == (s["t1"] - s["t0"], 6) and out[1].shape == (s["M"], 24 * 32)
+    assert rel_err(P.cpu(), r["P"], floor=1.0) < 1e-6 and rel_err(D.cpu(), r["D"], floor=1.0) < 1e-6
+    with pytest.raises(RuntimeError):
+        backends.ba(P, D, s["intrinsics"].to(dev), s["disps_sens"].to(dev), s["targets"].to(dev).permute(0, 1, 3, 2), s["weights"].to(dev),
+                    s["eta"].to(dev), s["ii"].to(dev), s["jj"].to(dev), s["t0"], s["t1"], 2, s["lm"], s["ep"], False)   # non-contiguous (src/droid.cpp:110)
+
+
+def test_ba_cholesky_failure_gives_zero_update(capi):
+    """non-SPD reduced system -> dx = 0 like the reference (src/droid_kernels.cu:1216-1219); forced with ep << 0"""
+    s = _scene(seed=13)
+    P, D = s["poses"].to(dev), s["disps"].to(dev)
+    dx, dz, M, st, _ = c_ba(capi, P, D, s["intrinsics"].to(dev), s["disps_sens"].to(dev), s["targets"].to(dev), s["weights"].to(dev),
+                            s["eta"].to(dev), s["ii"].to(dev), s["jj"].to(dev), s["t0"], s["t1"], 1, 0.0, -1e9, True, s["M"])
+    assert st & 4
+    assert float(dx.abs().max()) == 0.0 and torch.equal(P.cpu(), s["poses"])
