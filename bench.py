@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the dense-BA update hot path (BASELINE.json metric: "BA-update iters/sec (512 edges, 344x64x48) at
+1/2/4/8 B200; corr HBM GB/s vs peak").
+
+One STEP = the droid_backends work of one FactorGraph.update: a 4-level radius-3
+corr_index_forward over all edges + ba(iterations=2, lm=1e-4, ep=0.1) on a synthetic 512-edge / 72-keyframe graph at
+48x64 (fp16 correlation volumes as in the live system).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+* our arm: `value` times the step with all inputs resident in HBM, launched through the C ABI (ctypes); `e2e` goes
+  through the pybind `droid_backends` API from pinned HOST buffers (per-step inputs H2D, BA results D2H inside the timed
+  region; the correlation volumes are persistent device state exactly as in the reference, where they are produced on
+  the GPU once per edge and never cross PCIe).
+* N > 1 (torchrun, one rank per GPU): weak scaling in edges -- the graph has 512*N edges over the same 72-keyframe
+  window, sharded by source frame (droid_slam_b200/sharded.py); one NCCL all-reduce of the reduced pose system per
+  Gauss-Newton iteration; `value` = 512-edge-equivalents per second = N / step time (max over ranks).
+* --impl reference: the UNMODIFIED reference CUDA kernels (oracle/_ref/droid_backends_ref: /root/reference/src built for
+  sm_100a against the dense-LLT Eigen stand-in) on the same tensors, same protocol; corr_index is issued in chunks of
+  128 edges because the reference's 32-bit accessors cannot address a 512-edge level-0 volume.  Falls back to the CPU
+  oracle port when that build is absent.  Rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+EDGES_PER_GPU = 512
+FRAMES = 72
+HT, WD = 48, 64
+RADIUS, LEVELS = 3, 4
+BA_ITERS, LM, EP = 2, 1e-4, 0.1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f16", choices=["f16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index; self.proc = None; self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def roofline_traffic():
+    """dram bytes per step of the corr_index kernels from the committed ncu capture (profiles/), or None"""
+    p = os.path.join(ROOT, "profiles", "corr_index_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------------
+def build_problem(args, rank, world, dev):
+    """the rank's shard of the (512*world)-edge graph: BA tensors, correlation pyramid, lookup coordinates"""
+    from droid_slam_b200 import sharded, synth
+    cfg = dict(E=EDGES_PER_GPU * world, N=FRAMES, ht=HT, wd=WD, stereo=False, itrs=BA_ITERS, lm=LM, ep=EP)
+    s = synth.make_scene(cfg, seed=0)
+    bounds = sharded.partition_frames(s["ii"], FRAMES, world)
+    lo, hi = bounds[rank]
+    idx = sharded.shard_edges(s["ii"], lo, hi)
+    dtype = torch.float16 if args.dtype == "f16" else torch.float32
+    sub = dict(s); sub["ii"] = s["ii"][idx]; sub["jj"] = s["jj"][idx]; sub["coords_gt"] = s["coords_gt"][idx]
+    sub["cfg"] = dict(cfg, E=int(idx.numel()))
+    pyr, coords, _ = synth.make_corr_inputs(sub, dtype=dtype, device=dev, edge_chunk=32)
+    kx = torch.unique(torch.cat([torch.arange(s["t0"], s["t1"]), s["ii"]]))
+    eta_f = torch.zeros(FRAMES, HT, WD); eta_f[kx] = s["eta"]
+    host = dict(poses=s["poses"], disps=s["disps"], disps_sens=s["disps_sens"], intrinsics=s["intrinsics"], targets=s["targets"][idx].contiguous(),
+                weights=s["weights"][idx].contiguous(), eta=s["eta"], eta_by_frame=eta_f, ii=sub["ii"].contiguous(), jj=sub["jj"].contiguous(),
+                coords=coords.cpu())
+    return dict(scene=s, host=host, bounds=bounds, pyr=pyr, coords=coords, E=int(idx.numel()), dtype=dtype, t0=s["t0"], t1=s["t1"], M=s["M"])
+
+
+def alg_bytes_corr(E, dtype):
+    s = 2 if dtype == torch.float16 else 4
+    return E * HT * WD * (LEVELS * ((2 * RADIUS + 2) ** 2 + (2 * RADIUS + 1) ** 2) * s + LEVELS * 8)     # HW*(452 s + 32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, dev):
+    import droid_slam_b200
+    from droid_slam_b200 import c_api, sharded
+    be = droid_slam_b200.install()          # raises if the native extension is missing: no fallback
+    L = c_api.load()
+    pb = build_problem(args, rank, world, dev)
+    h = pb["host"]
+    E, dtype = pb["E"], pb["dtype"]
+    dcode = c_api.DBA_F16 if dtype == torch.float16 else c_api.DBA_F32
+    d = {k: v.to(dev) for k, v in h.items()}
+    pristine_poses, pristine_disps = d["poses"].clone(), d["disps"].clone()
+    coords_l = [(pb["coords"] / 2 ** l).contiguous() for l in range(LEVELS)]
+    corr_out = [torch.empty(E, 7, 7, HT, WD, dtype=dtype, device=dev) for _ in range(LEVELS)]
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    engine = sharded.CApiEngine(dev)
+    drv = sharded.ShardedBA(engine)
+
+    def step_resident(ev=None):
+        d["poses"].copy_(pristine_poses); d["disps"].copy_(pristine_disps)
+        if ev: ev[0].record()
+        for l in range(LEVELS):
+            v = pb["pyr"][l]
+            c_api.check(L.dba_corr_index_forward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(coords_l[l].data_ptr()),
+                                                 ctypes.c_void_p(corr_out[l].data_ptr()), E, HT, WD, v.shape[3], v.shape[4], RADIUS, dcode, sp), "corr")
+        if ev: ev[1].record()
+        drv.run(d["poses"], d["disps"], d["intrinsics"], d["disps_sens"], d["targets"], d["weights"], d["eta_by_frame"], d["ii"], d["jj"],
+                pb["t0"], pb["t1"], BA_ITERS, LM, EP, pb["bounds"], exchange_disps=(world > 1))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for k in range(args.steps):
+        step_resident(evs[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = t_beg.elapsed_time(t_end)
+    corr_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    t = torch.tensor([ms_total, corr_ms], device=dev, dtype=torch.float64)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t[0]) / args.steps
+    corr_ms = float(t[1])
+
+    # ---- end to end through the public pybind API from pinned host buffers
+    pin = {k: h[k].pin_memory() for k in ("coords", "targets", "weights", "eta", "eta_by_frame", "poses", "disps", "disps_sens", "ii", "jj", "intrinsics")}
+    P = pb["t1"] - pb["t0"]
+    out_pin = dict(poses=torch.empty(FRAMES, 7).pin_memory(), disps=torch.empty(FRAMES, HT, WD).pin_memory(), dx=torch.empty(P, 6).pin_memory())
+    h2d = sum(pin[k].numel() * pin[k].element_size() for k in ("coords", "targets", "weights", "poses", "disps", "disps_sens", "ii", "jj", "intrinsics"))
+    h2d += pin["eta"].numel() * 4 if world == 1 else pin["eta_by_frame"].numel() * 4
+    d2h = sum(v.numel() * v.element_size() for v in out_pin.values())
+
+    def step_e2e():
+        g = {k: pin[k].to(dev, non_blocking=True) for k in pin if k not in ("eta", "eta_by_frame")}
+        coords = g["coords"]
+        feats = []
+        for l in range(LEVELS):
+            corr, = be.corr_index_forward(pb["pyr"][l], coords / 2 ** l, RADIUS)       # reference call pattern, modules/corr.py:46-48
+            feats.append(corr)
+        if world == 1:
+            eta = pin["eta"].to(dev, non_blocking=True)
+            dx, dz = be.ba(g["poses"], g["disps"], g["intrinsics"], g["disps_sens"], g["targets"], g["weights"], eta, g["ii"], g["jj"],
+                           pb["t0"], pb["t1"], BA_ITERS, LM, EP, False)
+        else:
+            eta = pin["eta_by_frame"].to(dev, non_blocking=True)
+            drv.run(g["poses"], g["disps"], g["intrinsics"], g["disps_sens"], g["targets"], g["weights"], eta, g["ii"], g["jj"],
+                    pb["t0"], pb["t1"], BA_ITERS, LM, EP, pb["bounds"], exchange_disps=True)
+            dx = engine.dx
+        out_pin["poses"].copy_(g["poses"], non_blocking=True); out_pin["disps"].copy_(g["disps"], non_blocking=True)
+        out_pin["dx"].copy_(dx, non_blocking=True)
+        return feats
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[0]) / args.steps
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak()
+    alg = alg_bytes_corr(E, dtype)
+    achieved = alg / (corr_ms * 1e-3) / 1e9
+    traffic = roofline_traffic()
+    launches_per_step = LEVELS + 2 + BA_ITERS * 5        # corr x4, prepare+csr, per GN iter: build, schur, solve, backsub, pose_retr
+    line = {
+        "metric": "BA-update iters/sec (512 edges, 344x64x48)", "value": world * 1e3 / ms_step, "unit": "iters/s (512-edge equivalents)",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (BA solve in f64), %s corr volumes" % args.dtype, "data": "synthetic",
+        "impl": "ours",
+        "config": {"workload": "metric: %d edges/GPU x %d GPU(s) over a %d-keyframe window at %dx%d, 4-level r=3 corr_index_forward + ba(itrs=2, lm=1e-4, ep=0.1)"
+                               % (EDGES_PER_GPU, world, FRAMES, HT, WD),
+                   "edges_this_rank": E, "frames": FRAMES, "depth_frames": pb["M"], "pose_system": 6 * (pb["t1"] - pb["t0"]),
+                   "parallelism": "edge-sharded by source frame, 1 NCCL all-reduce of the %d-double pose system per GN iteration" % (36 * P * P + 6 * P) if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: %.1f GB of correlation volumes stream through the 126 MB L2 every step" % (sum(v.numel() * v.element_size() for v in pb["pyr"]) / 1e9)},
+        "e2e": {"value": world * 1e3 / e2e_ms, "unit": "iters/s (512-edge equivalents)", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "droid_backends.corr_index_forward x4 + droid_backends.ba from pinned host buffers; volumes persistent on device"},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": {"kernel": "corr_index_fwd_%s_r3_kernel (4 launches/step)" % args.dtype, "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                     "kernel_ms_per_step": corr_ms, "share_of_step": corr_ms / ms_step,
+                     "traffic": (traffic or {}).get("dram_bytes_per_step_" + args.dtype)},
+        "ba_ms_per_step": ms_step - corr_ms,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(pb)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline(pb, budget_edges=64):
+    """the CPU oracle (a port of the reference kernels, oracle/) on a bounded sample of the same step, host cores"""
+    import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h = pb["host"]
+    n = min(budget_edges, pb["E"])
+    vols = [v[:n].cpu() for v in pb["pyr"]]
+    coords = h["coords"][:n]
+    t0 = time.time()
+    for l, v in enumerate(vols):
+        oracle.corr_index_forward(v, coords / 2 ** l, RADIUS)
+    t_corr = (time.time() - t0) * pb["E"] / n
+    P, D = h["poses"].clone(), h["disps"].clone()
+    t0 = time.time()
+    oracle.ba(P, D, h["intrinsics"], h["disps_sens"], h["targets"], h["weights"], h["eta"], h["ii"], h["jj"], pb["t0"], pb["t1"], BA_ITERS, LM, EP, False)
+    t_ba = time.time() - t0
+    return {"value": 1.0 / (t_corr + t_ba), "unit": "iters/s", "cores": cores, "kind": "port",
+            "sample": "corr_index_forward oracle on %d of %d edges (4 levels, time scaled by edges) + full 512-edge ba(itrs=2) oracle, torch CPU threads=%d"
+                      % (n, pb["E"], cores), "corr_s": t_corr, "ba_s": t_ba}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world, dev):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    try:
+        import droid_backends_ref as ref
+    except Exception as e:                                   # reference build absent: the CPU oracle port is the reference arm
+        return run_reference_cpu(args, dev, "oracle/_ref not importable: %s" % str(e)[:80])
+    lib = ctypes.CDLL(ref.__file__)
+    lib.droid_ref_solve_seconds.restype = ctypes.c_double
+    pb = build_problem(args, 0, 1, dev)
+    h = pb["host"]
+    E = pb["E"]
+    d = {k: v.to(dev) for k, v in h.items()}
+    CH = 128
+
+    def corr_all(coords):
+        outs = []
+        for l in range(LEVELS):
+            c = coords / 2 ** l
+            parts = [ref.corr_index_forward(pb["pyr"][l][s:s + CH], c[s:s + CH].contiguous(), RADIUS)[0] for s in range(0, E, CH)]
+            outs.append(parts)
+        return outs
+
+    def step_resident():
+        P, D = d["poses"].clone(), d["disps"].clone()
+        corr_all(pb["coords"])
+        ref.ba(P, D, d["intrinsics"], d["disps_sens"], d["targets"], d["weights"], d["eta"], d["ii"], d["jj"], pb["t0"], pb["t1"], BA_ITERS, LM, EP, False)
+
+    pin = {k: h[k].pin_memory() for k in ("coords", "targets", "weights", "eta", "poses", "disps", "disps_sens", "ii", "jj", "intrinsics")}
+    Pn = pb["t1"] - pb["t0"]
+    out_pin = dict(poses=torch.empty(FRAMES, 7).pin_memory(), disps=torch.empty(FRAMES, HT, WD).pin_memory(), dx=torch.empty(Pn, 6).pin_memory())
+    h2d = sum(v.numel() * v.element_size() for v in pin.values()); d2h = sum(v.numel() * v.element_size() for v in out_pin.values())
+
+    def step_e2e():
+        g = {k: pin[k].to(dev, non_blocking=True) for k in pin}
+        corr_all(g["coords"])
+        dx, dz = ref.ba(g["poses"], g["disps"], g["intrinsics"], g["disps_sens"], g["targets"], g["weights"], g["eta"], g["ii"], g["jj"],
+                        pb["t0"], pb["t1"], BA_ITERS, LM, EP, False)
+        out_pin["poses"].copy_(g["poses"], non_blocking=True); out_pin["disps"].copy_(g["disps"], non_blocking=True); out_pin["dx"].copy_(dx, non_blocking=True)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm): fn()
+        torch.cuda.synchronize()
+        s0 = lib.droid_ref_solve_seconds()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time(); e0.record()
+        for _ in range(steps): fn()
+        e1.record(); torch.cuda.synchronize()
+        return max(e0.elapsed_time(e1), (time.time() - w0) * 1e3) / steps, (lib.droid_ref_solve_seconds() - s0) * 1e3 / steps
+
+    sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
+    ms_step, solve_ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop()
+    e2e_ms, _ = timed(step_e2e, args.steps, 2)
+    line = {
+        "metric": "BA-update iters/sec (512 edges, 344x64x48)", "value": 1e3 / ms_step, "unit": "iters/s (512-edge equivalents)", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (CPU solve in f64), %s corr volumes" % args.dtype, "data": "synthetic", "impl": "reference",
+        "config": {"workload": "metric: 512 edges over a %d-keyframe window at %dx%d, 4-level r=3 corr_index_forward (chunks of %d edges: 32-bit accessors) + ba(itrs=2)" % (FRAMES, HT, WD, CH),
+                   "implementation": "unmodified /root/reference/src/*.cu + droid.cpp built for sm_100a (oracle/build_ref.sh); CPU solve = dense fp64 LLT stand-in for Eigen::SimplicialLLT",
+                   "cpu_solve_ms_per_step": solve_ms, "ms_per_step_without_cpu_solve": ms_step - solve_ms},
+        "e2e": {"value": 1e3 / e2e_ms, "unit": "iters/s (512-edge equivalents)", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "cpu_baseline": {"value": 1e3 / ms_step, "unit": "iters/s", "cores": os.cpu_count(), "kind": "reference",
+                         "sample": "full workload, %d steps; the reference path is CUDA kernels + a host-side sparse-block solve (its CPU part uses 1 thread)" % args.steps},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def run_reference_cpu(args, dev, why):
+    import oracle  # noqa: F401
+    pb = build_problem(args, 0, 1, dev)
+    cb = cpu_baseline(pb)
+    ms = 1e3 / cb["value"]
+    print(json.dumps({"metric": "BA-update iters/sec (512 edges, 344x64x48)", "value": cb["value"], "unit": "iters/s (512-edge equivalents)", "n_gpus": 1,
+                      "steps": 1, "warmup": 0, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "impl": "reference", "config": {"workload": "metric (CPU oracle port; %s)" % why},
+                      "cpu_baseline": dict(cb, kind="port"), "e2e": {"value": cb["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world, dev)
+        else:
+            run_ours(args, rank, world, dev)
+    finally:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

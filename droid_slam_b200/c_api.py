@@ -26,6 +26,7 @@ class BAArgs(ctypes.Structure):
         ("dx_out", ctypes.c_void_p), ("dz_out", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("stream", ctypes.c_void_p),
+        ("own_lo", ctypes.c_int), ("own_hi", ctypes.c_int), ("eta_by_frame", ctypes.c_int),
     ]
 
 

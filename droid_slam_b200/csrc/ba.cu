@@ -180,7 +180,7 @@ __device__ __forceinline__ void adj_se3(const float* t, const float* q, const fl
 __global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
     const float* __restrict__ poses, const float* __restrict__ disps, const float* __restrict__ intr,
     const float* __restrict__ disps_sens, const float* __restrict__ targets, const float* __restrict__ weights,
-    const float* __restrict__ eta, int eta_rows, const int64_t* __restrict__ jj,
+    const float* __restrict__ eta, int eta_rows, int eta_by_frame, const int64_t* __restrict__ jj,
     const int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr, const int* __restrict__ edgeidx,
     int HW, int wd, int t0, int P, int motion_only,
     double* __restrict__ Hsys, double* __restrict__ bsys, float* __restrict__ Eij, float* __restrict__ Cout, float* __restrict__ wout,
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
   if (!motion_only) {
     // depth block:  C = sum Cii + m*alpha + (1-m)*eta ;  w = sum bz - m*alpha*(d - d_sens)   (reference :1405-1408)
     const float alpha = 0.05f;
-    const int erow = (eta_rows == 1) ? 0 : min(m, eta_rows - 1);
+    const int erow = (eta_rows == 1) ? 0 : min(eta_by_frame ? ix : m, eta_rows - 1);
 #pragma unroll
     for (int s = 0; s < kPPT; s++) {
       const int p = pix[s];
@@ -757,10 +757,11 @@ __global__ void __launch_bounds__(256) ba_backsub_kernel(
     const int64_t* __restrict__ jj, const int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
     const int* __restrict__ edgeidx, int HW, int t0, int P,
     const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
-    const float* __restrict__ dx, float* __restrict__ disps, float* __restrict__ dz_out) {
+    const float* __restrict__ dx, float* __restrict__ disps, float* __restrict__ dz_out, int own_lo, int own_hi) {
   const int m = blockIdx.y;
   if (m >= hdr[HDR_M]) return;
   const int ix = kx[m];
+  const bool owned = ix >= own_lo && ix < own_hi;   // edge-sharded runs: other ranks hold the out-edges of the other frames
   const int e_begin = rowptr[m], e_end = rowptr[m + 1];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
@@ -787,8 +788,8 @@ __global__ void __launch_bounds__(256) ba_backsub_kernel(
   }
   const float q = 1.0f / __ldg(Cin + (size_t)m * HW + p);
   const float dz = q * (__ldg(win + (size_t)m * HW + p) - dw);
-  dz_out[(size_t)m * HW + p] = dz;
-  disps[(size_t)ix * HW + p] += dz;       // K8 (:942-955)
+  dz_out[(size_t)m * HW + p] = owned ? dz : 0.f;
+  if (owned) disps[(size_t)ix * HW + p] += dz;       // K8 (:942-955)
 }
 
 __global__ void ba_pose_retr_kernel(float* __restrict__ poses, const float* __restrict__ dx, int t0, int P, float* __restrict__ dx_out) {
@@ -834,6 +835,8 @@ static int check_ba_args(const dba_ba_args* a, Layout& L) {
   DBA_CHECK_ARG(a->poses && a->disps && a->intrinsics && a->disps_sens, "null state pointer");
   DBA_CHECK_ARG(a->n_edges == 0 || (a->targets && a->weights && a->ii && a->jj), "null edge pointer");
   DBA_CHECK_ARG(a->motion_only || (a->eta && a->eta_rows >= 1), "eta missing");
+  DBA_CHECK_ARG(a->motion_only || !a->eta_by_frame || a->eta_rows >= a->n_frames, "eta_by_frame needs one eta row per frame");
+  DBA_CHECK_ARG(a->own_lo >= 0 && a->own_hi >= a->own_lo, "bad ownership range");
   DBA_CHECK_ARG(a->workspace != nullptr, "null workspace");
   DBA_CHECK_ARG(a->n_frames <= 65535, "more than 65535 frames");
   L = make_layout(a->n_frames, a->n_edges, a->ht, a->wd, a->t0, a->t1);
@@ -846,7 +849,7 @@ static int check_ba_args(const dba_ba_args* a, Layout& L) {
 extern "C" int dba_ba_prepare(const dba_ba_args* a) {
   Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)a->stream;
-  ba_prepare_kernel<<<1, 1024, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, a->t0, a->t1, a->motion_only ? 1 : a->eta_rows,
+  ba_prepare_kernel<<<1, 1024, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, a->t0, a->t1, (a->motion_only || a->eta_by_frame) ? 1 : a->eta_rows,
                                         WS(int, L.off_hdr), WS(int, L.off_frame2k), WS(int, L.off_kx), WS(int, L.off_rowptr));
   DBA_CHECK_LAUNCH("ba_prepare");
   if (a->n_edges > 0) {
@@ -867,7 +870,7 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
   double* bsys = Hsys + (size_t)L.n * L.n;
   dim3 grid((HW + kChunkPx - 1) / kChunkPx, a->n_frames);   // y: depth frames (CTAs beyond M exit immediately)
   ba_build_kernel<<<grid, kBuildThreads, 0, st>>>(a->poses, a->disps, a->intrinsics, a->disps_sens, a->targets, a->weights, a->eta,
-                                                  a->eta_rows, a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                  a->eta_rows, a->eta_by_frame, a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                   WS(int, L.off_edgeidx), HW, a->wd, a->t0, L.P, a->motion_only, Hsys, bsys,
                                                   WS(float, L.off_Eij), WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei));
   DBA_CHECK_LAUNCH("ba_build");
@@ -904,7 +907,7 @@ extern "C" int dba_ba_solve(const dba_ba_args* a) {
     dim3 grid((HW + 255) / 256, a->n_frames);
     ba_backsub_kernel<<<grid, 256, 0, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr), WS(int, L.off_edgeidx),
                                             HW, a->t0, L.P, WS(float, L.off_Eij), WS(float, L.off_C), WS(float, L.off_w),
-                                            WS(float, L.off_Ei), dx, a->disps, a->dz_out);
+                                            WS(float, L.off_Ei), dx, a->disps, a->dz_out, a->own_lo, a->own_hi);
     DBA_CHECK_LAUNCH("ba_backsub");
   }
   ba_pose_retr_kernel<<<(L.P + 127) / 128, 128, 0, st>>>(a->poses, dx, a->t0, L.P, a->dx_out);

@@ -80,6 +80,7 @@ std::vector<torch::Tensor> ba(torch::Tensor poses, torch::Tensor disps, torch::T
   a.lm = lm; a.ep = ep; a.motion_only = motion_only ? 1 : 0;
   a.dx_out = dx.data_ptr<float>(); a.dz_out = nullptr;
   a.workspace = ws.data_ptr(); a.workspace_bytes = ws_bytes; a.stream = cur_stream();
+  a.own_lo = 0; a.own_hi = n_frames; a.eta_by_frame = 0;
 
   torch::Tensor dz;
   if (!motion_only) {

@@ -13,7 +13,7 @@ __all__ = ["CONFIGS", "make_graph", "make_scene", "reproject", "make_corr_inputs
 CONFIGS = {
     "c1_plumbing": dict(E=24, N=8, ht=48, wd=64, stereo=False, itrs=3, lm=1e-4, ep=0.1),
     "c2_frontend": dict(E=128, N=25, ht=48, wd=64, stereo=False, itrs=2, lm=1e-4, ep=0.1),
-    "metric": dict(E=512, N=64, ht=48, wd=64, stereo=False, itrs=2, lm=1e-4, ep=0.1),
+    "metric": dict(E=512, N=72, ht=48, wd=64, stereo=False, itrs=2, lm=1e-4, ep=0.1),
     "c3_global": dict(E=2048, N=400, ht=48, wd=64, stereo=False, itrs=10, lm=1e-5, ep=1e-2),
     "c4_stereo": dict(E=256, N=64, ht=48, wd=64, stereo=True, itrs=2, lm=1e-4, ep=0.1),
     "c5_stress": dict(E=8192, N=1000, ht=72, wd=96, stereo=False, itrs=2, lm=1e-4, ep=0.1),

@@ -107,6 +107,11 @@ typedef struct {
   float* dx_out; float* dz_out;
   void* workspace; size_t workspace_bytes;
   dba_stream_t stream;
+  /* edge-sharded multi-GPU runs (one rank = the out-edges of a contiguous range of source frames):
+   * only depth frames in [own_lo, own_hi) get their inverse depth updated by dba_ba_solve (the other ranks own the
+   * rest); single-GPU callers pass own_lo = 0, own_hi = n_frames.  eta_by_frame != 0: eta has n_frames rows indexed by
+   * FRAME id instead of M rows in depth-frame order (a rank's local depth-frame set differs from the global one). */
+  int own_lo, own_hi, eta_by_frame;
 } dba_ba_args;
 
 int dba_ba_prepare(const dba_ba_args* a);
