@@ -10,6 +10,7 @@ SYMBOLS = [
     "dba_projmap", "dba_frame_distance", "dba_depth_filter", "dba_iproj",
     "dba_ba_workspace_bytes", "dba_ba_system_offset", "dba_ba_system_bytes",
     "dba_ba_prepare", "dba_ba_build", "dba_ba_solve", "dba_ba", "dba_ba_read_info",
+    "dba_solve_workspace_bytes", "dba_solve_spd",
 ]
 
 DBA_F32, DBA_F16, DBA_F64, DBA_BF16 = 0, 1, 2, 3
@@ -62,6 +63,9 @@ def load():
         getattr(L, n).argtypes = [ctypes.POINTER(BAArgs)]
     L.dba_ba.argtypes = [ctypes.POINTER(BAArgs), ci]
     L.dba_ba_read_info.argtypes = [ctypes.POINTER(BAArgs), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.dba_solve_workspace_bytes.restype = ctypes.c_size_t
+    L.dba_solve_workspace_bytes.argtypes = [ci]
+    L.dba_solve_spd.argtypes = [vp, vp, ci, cf, cf, vp, vp, vp, ctypes.c_size_t, vp]
     _LIB = L
     return L
 

@@ -27,7 +27,6 @@ constexpr int kPPT = 4;            // pixels per thread in the build kernel
 constexpr int kBuildThreads = 256;
 constexpr int kChunkPx = kPPT * kBuildThreads;   // 1024 pixels per CTA
 constexpr int kEdgeBatch = 16;     // edges whose transforms / partial sums live in shared memory at once
-constexpr int kTile = 32;          // Cholesky tile
 
 struct Layout {
   size_t off_hdr, off_frame2k, off_kx, off_rowptr, off_edgeidx, off_sys, off_L, off_dx, off_Eij, off_C, off_w, off_Ei, total;
@@ -41,7 +40,6 @@ __host__ inline Layout make_layout(int N, int E, int ht, int wd, int t0, int t1)
   const size_t HW = (size_t)ht * wd;
   L.P = t1 - t0 > 0 ? t1 - t0 : 0;
   L.n = 6 * L.P;
-  const size_t npad = (size_t)((L.n + kTile - 1) / kTile) * kTile;
   size_t o = 0;
   L.off_hdr = o;      o = align_up(o + 64 * sizeof(int), 256);
   L.off_frame2k = o;  o = align_up(o + (size_t)(N + 1) * sizeof(int), 256);
@@ -49,7 +47,7 @@ __host__ inline Layout make_layout(int N, int E, int ht, int wd, int t0, int t1)
   L.off_rowptr = o;   o = align_up(o + (size_t)(N + 2) * sizeof(int), 256);
   L.off_edgeidx = o;  o = align_up(o + (size_t)(E + 1) * sizeof(int), 256);
   L.off_sys = o;      o = align_up(o + ((size_t)L.n * L.n + L.n) * sizeof(double), 256);
-  L.off_L = o;        o = align_up(o + (npad * npad + 2 * npad) * sizeof(double), 256);
+  L.off_L = o;        o = align_up(o + chol_workspace_bytes(L.n), 256);
   L.off_dx = o;       o = align_up(o + (size_t)(L.n + 6) * sizeof(float), 256);
   L.off_Eij = o;      o = align_up(o + (size_t)E * 6 * HW * sizeof(float), 256);
   const size_t Mmax = (size_t)N;   // at most one depth frame per buffer frame
@@ -139,20 +137,24 @@ __global__ void __launch_bounds__(1024) ba_prepare_kernel(const int64_t* __restr
   }
 }
 
-// stable placement of every edge inside its source frame's segment: rank = #earlier edges with the same source
+// stable placement of every edge inside its source frame's segment: rank = #earlier edges with the same source.
+// One warp per edge, lanes stride over the earlier edges (E^2/2 compares spread over E warps).
 __global__ void __launch_bounds__(256) ba_fill_csr_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int E, int N,
                                                           const int* __restrict__ frame2k, const int* __restrict__ rowptr,
                                                           int* __restrict__ edgeidx) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (e >= E) return;
   const long long i = ii[e], j = jj[e];
   if (i < 0 || i >= N || j < 0 || j >= N) return;
   int rank = 0;
-  for (int f = 0; f < e; f++) {
+  for (int f = lane; f < e; f += 32) {
     const long long i2 = ii[f], j2 = jj[f];
     rank += (i2 == i && j2 >= 0 && j2 < N) ? 1 : 0;
   }
-  edgeidx[rowptr[frame2k[i]] + rank] = e;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  if (lane == 0) edgeidx[rowptr[frame2k[i]] + rank] = e;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -375,15 +377,39 @@ __global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
 
 // ---------------------------------------------------------------------------------------------------------
 // Schur complement:  Hsys -= sum_k E_k Q_k E_k^T ,  bsys -= sum_k E_k Q_k w_k       (reference K9/K10 + schur_block)
-// rows of frame k: row 0 = (pose k, Ei_k) if k in [t0,t1); row 1+a = (pose jj[e_a], Eij[e_a]); rows whose pose is
-// outside [t0,t1) are dropped.  One CTA per (frame, pixel chunk); a thread owns one 6x6 block pair (r <= r').
+// rows of frame k: (pose k, Ei_k) if k is in [t0,t1), then (pose jj[e], Eij[e]) for the out-edges e of k; rows whose pose
+// is outside [t0,t1) are dropped (they contribute nothing, reference :1155,:1257).
+// One CTA per (frame, pixel chunk).  The rows are staged tile by tile (256 pixels) into shared memory with 128-bit
+// coalesced loads; a WARP owns a 6x6 block pair (r <= r'), its lanes split the pixels of the tile, the 36(+6) partial sums
+// are combined with a transpose-reduction (31 shuffles for 32 values) into a shared accumulator that the pair's owner
+// alone touches (no atomics, deterministic), and the CTA flushes its block pairs once with fp64 atomics into the LOWER
+// triangle of the reduced system.  kSingle: all rows fit one 12-row block (86 KB smem, 2 CTAs/SM); otherwise the
+// frame is processed as pairs of row blocks.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSchurThreads = 128;
-constexpr int kSchurTP = 64;        // pixels per shared-memory sub tile
-constexpr int kSchurMaxRows = 24;   // rows per pass; larger out-degrees are processed in several row-block passes
+constexpr int kSchurThreads = 256;
+constexpr int kSchurWarps = kSchurThreads / 32;
+constexpr int kSchurTP = 256;        // pixels per shared-memory tile
+constexpr int kSchurRB = 12;         // rows per block
+constexpr int kSchurMaxRows = 255;   // rows per frame (out-degree + 1); larger frames raise ST_BAD_INDEX
 
+// total of value i ends up in lane i  (v[0] on return), 31 shuffles
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; i++) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <bool kSingle>
 __global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
-    const int64_t* __restrict__ jj, const int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
+    const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
     const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
     const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
     double* __restrict__ Hsys, double* __restrict__ bsys) {
@@ -392,325 +418,160 @@ __global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
   const int ix = kx[m];
   const int e_begin = rowptr[m];
   const int deg = rowptr[m + 1] - e_begin;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = 6 * P;
 
-  // active rows (pose inside the window)
-  __shared__ int s_rowpose[kSchurMaxRows * 2];
-  __shared__ const float* s_rowptr[kSchurMaxRows * 2];
-  __shared__ int s_nrows_total;
-  extern __shared__ float s_dyn[];   // [2 row blocks][kSchurTP][stride] + Q[kSchurTP] + Qw[kSchurTP]
+  __shared__ int s_pose[kSchurMaxRows + 1];
+  __shared__ const float* s_ptr[kSchurMaxRows + 1];
+  __shared__ int s_nrows;
+  extern __shared__ float s_dyn[];
 
-  // The row list can be longer than kSchurMaxRows: process row-block pairs (bi <= bj)
-  // First count the active rows.
-  int nrows = 0;
-  {
-    // serial count by thread 0 (deg is small); rows are indexed on the fly by `nth_row`
-    if (tid == 0) {
-      int c = 0;
-      if (ix >= t0 && ix < t0 + P) c++;
-      for (int a = 0; a < deg; a++) { const int pj = (int)jj[edgeidx[e_begin + a]] - t0; if (pj >= 0 && pj < P) c++; }
-      s_nrows_total = c;
+  if (tid == 0) {
+    int c = 0;
+    if (ix >= t0 && ix < t0 + P) { s_pose[c] = ix - t0; s_ptr[c] = Eiin + (size_t)m * 6 * HW; c++; }
+    for (int a = 0; a < deg; a++) {
+      const int e = edgeidx[e_begin + a];
+      const int pj = (int)jj[e] - t0;
+      if (pj >= 0 && pj < P) {
+        if (c < kSchurMaxRows) { s_pose[c] = pj; s_ptr[c] = Eij + (size_t)e * 6 * HW; c++; }
+        else atomicOr(&hdr[HDR_STATUS], ST_BAD_INDEX);
+      }
     }
-    __syncthreads();
-    nrows = s_nrows_total;
+    s_nrows = c;
   }
+  __syncthreads();
+  const int nrows = s_nrows;
   if (nrows == 0) return;
-  const int nblk = (nrows + kSchurMaxRows - 1) / kSchurMaxRows;
-  const int stride = 6 * kSchurMaxRows + 2;   // even (8-byte aligned LDS.64), != 0 mod 32
-  float* sA = s_dyn;                              // row block bi
-  float* sB = s_dyn + (size_t)kSchurTP * stride;  // row block bj
-  float* sQ = sB + (size_t)kSchurTP * stride;
-  float* sQw = sQ + kSchurTP;
+  if (kSingle != (nrows <= kSchurRB)) return;       // the other instantiation owns this frame
 
+  const int nblk = (nrows + kSchurRB - 1) / kSchurRB;
+  constexpr int kRowFloats = 6 * kSchurTP;           // one row of a tile: [6][TP]
+  float* sA = s_dyn;                                  // [RB][6][TP]
+  float* sB = kSingle ? sA : sA + kSchurRB * kRowFloats;
+  float* sQ = (kSingle ? sA + kSchurRB * kRowFloats : sB + kSchurRB * kRowFloats);
+  float* sQw = sQ + kSchurTP;
+  float* sS = sQw + kSchurTP;                         // [pairs][42]: 36 block entries + 6 rhs entries
   const int px_begin = blockIdx.x * px_per_cta;
   const int px_end = min(HW, px_begin + px_per_cta);
+  if (px_begin >= px_end) return;
+  const bool vec4 = (HW % 4) == 0;
 
   for (int bi = 0; bi < nblk; bi++) {
     for (int bj = bi; bj < nblk; bj++) {
-      __syncthreads();
-      // ---- resolve the rows of the two blocks (thread 0 walks the list; tiny)
-      if (tid == 0) {
-        int c = 0;
-        auto put = [&](int pose, const float* ptr) {
-          const int blk = c / kSchurMaxRows, pos = c - blk * kSchurMaxRows;
-          if (blk == bi) { s_rowpose[pos] = pose; s_rowptr[pos] = ptr; }
-          if (blk == bj) { s_rowpose[kSchurMaxRows + pos] = pose; s_rowptr[kSchurMaxRows + pos] = ptr; }
-          c++;
-        };
-        if (ix >= t0 && ix < t0 + P) put(ix - t0, Eiin + (size_t)m * 6 * HW);
-        for (int a = 0; a < deg; a++) {
-          const int e = edgeidx[e_begin + a];
-          const int pj = (int)jj[e] - t0;
-          if (pj >= 0 && pj < P) put(pj, Eij + (size_t)e * 6 * HW);
-        }
-      }
-      __syncthreads();
-      const int ra = min(kSchurMaxRows, nrows - bi * kSchurMaxRows);
-      const int rb = min(kSchurMaxRows, nrows - bj * kSchurMaxRows);
-      // pairs: bi == bj -> r <= r' ; else all (r, r')
+      const int ra = min(kSchurRB, nrows - bi * kSchurRB);
+      const int rb = min(kSchurRB, nrows - bj * kSchurRB);
       const int npairs = (bi == bj) ? ra * (ra + 1) / 2 : ra * rb;
-      for (int pbase = 0; pbase < npairs; pbase += kSchurThreads) {
-        const int pr = pbase + tid;
-        int r = 0, r2 = 0;
-        const bool active = pr < npairs;
-        if (active) {
-          if (bi == bj) {   // unrank lower-triangular pair index: pr = r2*(r2+1)/2 + r, r <= r2
+      __syncthreads();
+      for (int k = tid; k < npairs * 42; k += kSchurThreads) sS[k] = 0.f;
+
+      for (int p0 = px_begin; p0 < px_end; p0 += kSchurTP) {
+        const int np = min(kSchurTP, px_end - p0);
+        __syncthreads();
+        // ---- stage the rows of block bi (and bj): one warp per (row, component) line of 256 pixels
+        const int nlines = (ra + ((bi == bj) ? 0 : rb)) * 6;
+        for (int ln = warp; ln < nlines; ln += kSchurWarps) {
+          const int rowl = ln / 6, c = ln - rowl * 6;
+          const bool second = rowl >= ra;
+          const int row = second ? (bj * kSchurRB + rowl - ra) : (bi * kSchurRB + rowl);
+          float* dst = (second ? sB + (rowl - ra) * kRowFloats : sA + rowl * kRowFloats) + c * kSchurTP;
+          const float* src = s_ptr[row] + (size_t)c * HW + p0;
+          if (vec4 && np == kSchurTP) {
+#pragma unroll
+            for (int h = 0; h < kSchurTP / 128; h++) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(src) + h * 32 + lane);
+              reinterpret_cast<float4*>(dst)[h * 32 + lane] = v;
+            }
+          } else {
+            for (int px = lane; px < kSchurTP; px += 32) dst[px] = (px < np) ? __ldg(src + px) : 0.f;
+          }
+        }
+        for (int px = tid; px < kSchurTP; px += kSchurThreads) {
+          float q = 0.f, qw = 0.f;
+          if (px < np) { q = 1.0f / __ldg(Cin + (size_t)m * HW + p0 + px); qw = q * __ldg(win + (size_t)m * HW + p0 + px); }
+          sQ[px] = q; sQw[px] = qw;
+        }
+        __syncthreads();
+        // ---- block pairs: one warp per pair, lanes split the pixels
+        for (int pr = warp; pr < npairs; pr += kSchurWarps) {
+          int r, r2;
+          if (bi == bj) {
             r2 = (int)((sqrtf(8.f * (float)pr + 1.f) - 1.f) * 0.5f);
             while (r2 * (r2 + 1) / 2 > pr) r2--;
             while ((r2 + 1) * (r2 + 2) / 2 <= pr) r2++;
             r = pr - r2 * (r2 + 1) / 2;
           } else { r = pr / rb; r2 = pr - r * rb; }
-        }
-        float acc[36], bacc[6];
+          const float* rowA = sA + r * kRowFloats;
+          const float* rowB = ((bi == bj) ? sA : sB) + r2 * kRowFloats;
+          const bool diag = (bi == bj) && (r == r2);
+          float acc[36], bacc[6];
 #pragma unroll
-        for (int k = 0; k < 36; k++) acc[k] = 0.f;
+          for (int k = 0; k < 36; k++) acc[k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 6; k++) bacc[k] = 0.f;
-
-        for (int p0 = px_begin; p0 < px_end; p0 += kSchurTP) {
-          const int np = min(kSchurTP, px_end - p0);
-          __syncthreads();
-          // stage rows: sA[px][row*6+c], sB likewise; Q and Q*w
-          for (int k = tid; k < ra * 6 * kSchurTP; k += kSchurThreads) {
-            const int px = k % kSchurTP, rc = k / kSchurTP;
-            const int row = rc / 6, c = rc - row * 6;
-            sA[px * stride + rc] = (px < np) ? __ldg(s_rowptr[row] + (size_t)c * HW + p0 + px) : 0.f;
-          }
-          if (bj != bi) {
-            for (int k = tid; k < rb * 6 * kSchurTP; k += kSchurThreads) {
-              const int px = k % kSchurTP, rc = k / kSchurTP;
-              const int row = rc / 6, c = rc - row * 6;
-              sB[px * stride + rc] = (px < np) ? __ldg(s_rowptr[kSchurMaxRows + row] + (size_t)c * HW + p0 + px) : 0.f;
+          for (int k = 0; k < 6; k++) bacc[k] = 0.f;
+#pragma unroll 2
+          for (int px = lane; px < kSchurTP; px += 32) {
+            const float q = sQ[px];
+            float ea[6], eb[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) { ea[c] = rowA[c * kSchurTP + px]; eb[c] = rowB[c * kSchurTP + px]; }
+            if (diag) {
+              const float qw = sQw[px];
+#pragma unroll
+              for (int c = 0; c < 6; c++) bacc[c] += qw * ea[c];
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+              const float eq = ea[a] * q;             // ei[n] = E*q   (reference :1039)
+#pragma unroll
+              for (int c = 0; c < 6; c++) acc[a * 6 + c] += eq * eb[c];
             }
           }
-          for (int px = tid; px < kSchurTP; px += kSchurThreads) {
-            float q = 0.f, qw = 0.f;
-            if (px < np) { q = 1.0f / __ldg(Cin + (size_t)m * HW + p0 + px); qw = q * __ldg(win + (size_t)m * HW + p0 + px); }
-            sQ[px] = q; sQw[px] = qw;
-          }
-          __syncthreads();
-          if (active) {
-            const float* rowA = sA + r * 6;
-            const float* rowB = ((bi == bj) ? sA : sB) + r2 * 6;
-            for (int px = 0; px < np; px++) {
-              const float q = sQ[px];
-              const float2 a01 = *reinterpret_cast<const float2*>(rowA + px * stride);
-              const float2 a23 = *reinterpret_cast<const float2*>(rowA + px * stride + 2);
-              const float2 a45 = *reinterpret_cast<const float2*>(rowA + px * stride + 4);
-              const float2 b01 = *reinterpret_cast<const float2*>(rowB + px * stride);
-              const float2 b23 = *reinterpret_cast<const float2*>(rowB + px * stride + 2);
-              const float2 b45 = *reinterpret_cast<const float2*>(rowB + px * stride + 4);
-              const float ea[6] = {a01.x * q, a01.y * q, a23.x * q, a23.y * q, a45.x * q, a45.y * q};   // ei[n] = E*q (reference :1039)
-              const float eb[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+          // combine the lanes: values 0..31 by transpose-reduction, 32..35 (+ rhs) by butterflies
+          float v32[32];
 #pragma unroll
-              for (int a = 0; a < 6; a++)
+          for (int k = 0; k < 32; k++) v32[k] = acc[k];
+          const float tot = transpose_reduce32(v32, lane);
+          float* dstS = sS + pr * 42;
+          dstS[lane] += tot;
+          float t4[4] = {warp_sum(acc[32]), warp_sum(acc[33]), warp_sum(acc[34]), warp_sum(acc[35])};
+          if (lane < 4) dstS[32 + lane] += (lane == 0) ? t4[0] : (lane == 1) ? t4[1] : (lane == 2) ? t4[2] : t4[3];
+          if (diag) {
+            float t6[6];
 #pragma unroll
-                for (int c = 0; c < 6; c++) acc[a * 6 + c] += ea[a] * eb[c];
-              if (bi == bj && r == r2) {
-                const float qw = sQw[px];
-                bacc[0] += qw * a01.x; bacc[1] += qw * a01.y; bacc[2] += qw * a23.x;
-                bacc[3] += qw * a23.y; bacc[4] += qw * a45.x; bacc[5] += qw * a45.y;
-              }
-            }
+            for (int c = 0; c < 6; c++) t6[c] = warp_sum(bacc[c]);
+            if (lane < 6) dstS[36 + lane] += (lane == 0) ? t6[0] : (lane == 1) ? t6[1] : (lane == 2) ? t6[2] : (lane == 3) ? t6[3] : (lane == 4) ? t6[4] : t6[5];
           }
         }
-        if (active) {
-          const int pa = s_rowpose[r];
-          const int pb = s_rowpose[((bi == bj) ? 0 : kSchurMaxRows) + r2];
-          const bool same_row = (bi == bj) && (r == r2);
-#pragma unroll
-          for (int a = 0; a < 6; a++) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) {
-              const double v = (double)acc[a * 6 + c];
-              atomicAdd(&Hsys[(size_t)(pa * 6 + a) * n + pb * 6 + c], -v);
-              if (!same_row) atomicAdd(&Hsys[(size_t)(pb * 6 + c) * n + pa * 6 + a], -v);
-            }
-          }
+      }
+      __syncthreads();
+      // ---- flush: lower triangle of the reduced system
+      for (int k = tid; k < npairs * 42; k += kSchurThreads) {
+        const int pr = k / 42, o = k - pr * 42;
+        int r, r2;
+        if (bi == bj) {
+          r2 = (int)((sqrtf(8.f * (float)pr + 1.f) - 1.f) * 0.5f);
+          while (r2 * (r2 + 1) / 2 > pr) r2--;
+          while ((r2 + 1) * (r2 + 2) / 2 <= pr) r2++;
+          r = pr - r2 * (r2 + 1) / 2;
+        } else { r = pr / rb; r2 = pr - r * rb; }
+        const int pa = s_pose[bi * kSchurRB + r], pb = s_pose[bj * kSchurRB + r2];
+        const bool same_row = (bi == bj) && (r == r2);
+        const double v = -(double)sS[k];
+        if (o < 36) {
+          const int a = o / 6, c = o - a * 6;
+          const int gr = pa * 6 + a, gc = pb * 6 + c;       // S block (pa,pb)[a][c]; its transpose sits at (pb,pa)[c][a]
           if (same_row) {
-#pragma unroll
-            for (int a = 0; a < 6; a++) atomicAdd(&bsys[pa * 6 + a], -(double)bacc[a]);
+            if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+          } else {
+            if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+            if (gc >= gr) atomicAdd(&Hsys[(size_t)gc * n + gr], v);
           }
+        } else if (same_row) {
+          atomicAdd(&bsys[pa * 6 + (o - 36)], v);
         }
       }
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// solve: L = Hsys with damping; tiled fp64 Cholesky (single CTA, v1); dx = L^-T L^-1 bsys
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kSolveThreads = 256;
-
-// warp-level Cholesky of one 32x32 tile held one row per lane.  Returns false on a non-positive pivot.
-__device__ __forceinline__ bool warp_potrf32(double (&a)[kTile], int lane, int valid) {
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < kTile; k++) {
-    double d = __shfl_sync(0xffffffffu, a[k], k);
-    if (k >= valid) d = 1.0;            // padding rows/cols behave like identity
-    if (!(d > 0.0)) ok = false;
-    const double l_kk = sqrt(d);
-    const double r = 1.0 / l_kk;
-    const double l = (lane == k) ? l_kk : a[k] * r;   // column k, rows >= k (rows < k hold garbage that is never used)
-    a[k] = l;
-#pragma unroll
-    for (int j = k + 1; j < kTile; j++) {
-      const double ljk = __shfl_sync(0xffffffffu, l, j);
-      a[j] -= l * ljk;                  // only rows >= j matter
-    }
-  }
-  return ok;
-}
-
-__global__ void __launch_bounds__(kSolveThreads, 1) ba_solve_kernel(const double* __restrict__ Hsys, const double* __restrict__ bsys,
-                                                                 double* __restrict__ Lbuf, int n, float lm, float ep,
-                                                                 int* __restrict__ hdr, float* __restrict__ dx) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = kSolveThreads / 32;
-  const int nt = (n + kTile - 1) / kTile;
-  const int np = nt * kTile;
-  double* L = Lbuf;                       // [np][np] row-major, lower triangle used
-  double* y = Lbuf + (size_t)np * np;     // [np]
-  __shared__ double s_Lkk[kTile][kTile + 1];
-  __shared__ double s_rdiag[kTile];
-  __shared__ int s_fail;
-  if (tid == 0) s_fail = 0;
-
-  // ---- copy lower triangle with damping (reference SparseBlock::solve :1205-1206: diag += ep + lm*diag, in fp64)
-  const double lm64 = (double)lm, ep64 = (double)ep;
-  for (size_t idx = tid; idx < (size_t)np * np; idx += kSolveThreads) {
-    const int r = (int)(idx / np), c = (int)(idx - (size_t)r * np);
-    double v = 0.0;
-    if (r < n && c < n && c <= r) {
-      v = Hsys[(size_t)r * n + c];
-      if (r == c) v += ep64 + lm64 * v;
-    } else if (r == c) v = 1.0;
-    L[idx] = v;
-  }
-  for (int i = tid; i < np; i += kSolveThreads) y[i] = (i < n) ? bsys[i] : 0.0;
-  __syncthreads();
-
-  for (int k = 0; k < nt; k++) {
-    // (a) potrf of the diagonal tile by warp 0
-    if (warp == 0) {
-      double a[kTile];
-#pragma unroll
-      for (int c = 0; c < kTile; c++) a[c] = L[(size_t)(k * kTile + lane) * np + k * kTile + c];
-      const bool ok = warp_potrf32(a, lane, kTile);
-      if (!ok && lane == 0) s_fail = 1;
-#pragma unroll
-      for (int c = 0; c < kTile; c++) {
-        const double v = (c <= lane) ? a[c] : 0.0;
-        s_Lkk[lane][c] = v;
-        L[(size_t)(k * kTile + lane) * np + k * kTile + c] = v;
-      }
-      // reciprocal diagonal: a[lane] of lane `lane`
-      double dg = 0.0;
-#pragma unroll
-      for (int c = 0; c < kTile; c++) if (c == lane) dg = a[c];
-      s_rdiag[lane] = 1.0 / dg;
-    }
-    __syncthreads();
-    if (s_fail) break;
-    // (b) TRSM: tiles (i,k), i > k: one warp per tile, lane = row:  X L_kk^T = A
-    for (int i = k + 1 + warp; i < nt; i += NW) {
-      double a[kTile];
-      double* rowp = L + (size_t)(i * kTile + lane) * np + k * kTile;
-#pragma unroll
-      for (int c = 0; c < kTile; c++) a[c] = rowp[c];
-#pragma unroll
-      for (int c = 0; c < kTile; c++) {
-        const double x = a[c] * s_rdiag[c];
-        a[c] = x;
-#pragma unroll
-        for (int j = c + 1; j < kTile; j++) a[j] -= x * s_Lkk[j][c];
-        asm volatile("" ::: "memory");   // keep the 496 broadcast loads from being hoisted (register spills)
-      }
-#pragma unroll
-      for (int c = 0; c < kTile; c++) rowp[c] = a[c];
-    }
-    __syncthreads();
-    // (c) trailing update: tiles (i,j), k < j <= i:  A_ij -= L_ik L_jk^T ; one warp per tile, lane = row of (i,j)
-    const int rem = nt - k - 1;
-    const int ntiles = rem * (rem + 1) / 2;
-    for (int t = warp; t < ntiles; t += NW) {
-      int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-      while (bi * (bi + 1) / 2 > t) bi--;
-      while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
-      const int bj = t - bi * (bi + 1) / 2;
-      const int i = k + 1 + bi, j = k + 1 + bj;
-      double lik[kTile];
-      const double* lrow = L + (size_t)(i * kTile + lane) * np + k * kTile;
-#pragma unroll
-      for (int c = 0; c < kTile; c++) lik[c] = lrow[c];
-      double* crow = L + (size_t)(i * kTile + lane) * np + j * kTile;
-      const double* ljk = L + (size_t)(j * kTile) * np + k * kTile;
-      for (int c = 0; c < kTile; c++) {       // column c of tile (i,j) uses row c of tile (j,k) (broadcast loads)
-        double s = 0.0;
-        const double* lj = ljk + (size_t)c * np;
-#pragma unroll
-        for (int q = 0; q < kTile; q++) s += lik[q] * lj[q];
-        crow[c] -= s;
-      }
-    }
-    __syncthreads();
-  }
-
-  if (s_fail) {     // reference: solver.info() != Success -> dx = 0
-    if (tid == 0) { hdr[HDR_CHOL_FAIL] = 1; atomicOr(&hdr[HDR_STATUS], ST_CHOL_FAIL); }
-    for (int i = tid; i < n; i += kSolveThreads) dx[i] = 0.f;
-    return;
-  }
-  if (tid == 0) hdr[HDR_CHOL_FAIL] = 0;
-
-  // ---- forward substitution L y = b (tile by tile)
-  for (int k = 0; k < nt; k++) {
-    if (warp == 0) {
-      double yk = y[k * kTile + lane];
-      const double* lrow = L + (size_t)(k * kTile + lane) * np + k * kTile;
-      for (int c = 0; c < kTile; c++) {
-        const double lcc = __shfl_sync(0xffffffffu, lrow[c], c);   // lane c holds L[c][c] when reading its own row
-        double yc = __shfl_sync(0xffffffffu, yk, c) / lcc;
-        if (lane == c) yk = yc;
-        else if (lane > c) yk -= lrow[c] * yc;
-      }
-      y[k * kTile + lane] = yk;
-    }
-    __syncthreads();
-    for (int i = k + 1 + warp; i < nt; i += NW) {
-      const double* lrow = L + (size_t)(i * kTile + lane) * np + k * kTile;
-      double s = 0.0;
-#pragma unroll
-      for (int c = 0; c < kTile; c++) s += lrow[c] * y[k * kTile + c];
-      y[i * kTile + lane] -= s;
-    }
-    __syncthreads();
-  }
-  // ---- backward substitution L^T x = y
-  for (int k = nt - 1; k >= 0; k--) {
-    if (warp == 0) {
-      double xk = y[k * kTile + lane];
-      // column access of the diagonal tile: L[c][lane] for c >= lane
-      for (int c = kTile - 1; c >= 0; c--) {
-        const double lcc = L[(size_t)(k * kTile + c) * np + k * kTile + c];
-        double xc = __shfl_sync(0xffffffffu, xk, c) / lcc;
-        if (lane == c) xk = xc;
-        else if (lane < c) xk -= L[(size_t)(k * kTile + c) * np + k * kTile + lane] * xc;
-      }
-      y[k * kTile + lane] = xk;
-    }
-    __syncthreads();
-    // x_i -= L_ki^T x_k for i < k : lane = column of tile (k,i)
-    for (int i = warp; i < k; i += NW) {
-      double s = 0.0;
-      for (int c = 0; c < kTile; c++) s += L[(size_t)(k * kTile + c) * np + i * kTile + lane] * y[k * kTile + c];
-      y[i * kTile + lane] -= s;
-    }
-    __syncthreads();
-  }
-  for (int i = tid; i < n; i += kSolveThreads) dx[i] = (float)y[i];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -792,8 +653,10 @@ __global__ void __launch_bounds__(256) ba_backsub_kernel(
   if (owned) disps[(size_t)ix * HW + p] += dz;       // K8 (:942-955)
 }
 
-__global__ void ba_pose_retr_kernel(float* __restrict__ poses, const float* __restrict__ dx, int t0, int P, float* __restrict__ dx_out) {
+__global__ void ba_pose_retr_kernel(float* __restrict__ poses, const float* __restrict__ dx, int t0, int P, float* __restrict__ dx_out,
+                                    int* __restrict__ hdr) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0 && hdr[HDR_CHOL_FAIL]) atomicOr(&hdr[HDR_STATUS], ST_CHOL_FAIL);   // sticky: some iteration was not SPD (its dx is 0)
   if (k >= P) return;
   float xi[6], t[3], q[4], dt[3] = {0, 0, 0}, dq[4] = {0, 0, 0, 1}, t1[3], q1[4];
   float* ps = poses + 7 * (size_t)(t0 + k);
@@ -853,7 +716,7 @@ extern "C" int dba_ba_prepare(const dba_ba_args* a) {
                                         WS(int, L.off_hdr), WS(int, L.off_frame2k), WS(int, L.off_kx), WS(int, L.off_rowptr));
   DBA_CHECK_LAUNCH("ba_prepare");
   if (a->n_edges > 0) {
-    ba_fill_csr_kernel<<<(a->n_edges + 255) / 256, 256, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, WS(int, L.off_frame2k),
+    ba_fill_csr_kernel<<<(a->n_edges + 7) / 8, 256, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, WS(int, L.off_frame2k),
                                                                   WS(int, L.off_rowptr), WS(int, L.off_edgeidx));
     DBA_CHECK_LAUNCH("ba_fill_csr");
   }
@@ -875,19 +738,27 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
                                                   WS(float, L.off_Eij), WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei));
   DBA_CHECK_LAUNCH("ba_build");
   if (!a->motion_only) {
-    const int chunks = 2;
-    const int px_per_cta = ((HW + chunks - 1) / chunks + kSchurTP - 1) / kSchurTP * kSchurTP;
+    const int tiles = (HW + kSchurTP - 1) / kSchurTP;
+    int chunks = (2 * 148 + a->n_frames - 1) / a->n_frames;          // about two CTAs per SM worth of (frame, chunk) work items
+    chunks = chunks < 1 ? 1 : (chunks > tiles ? tiles : chunks);
+    const int px_per_cta = ((tiles + chunks - 1) / chunks) * kSchurTP;
     dim3 g2((HW + px_per_cta - 1) / px_per_cta, a->n_frames);
-    const size_t smem = ((size_t)2 * kSchurTP * (6 * kSchurMaxRows + 2) + 2 * kSchurTP) * sizeof(float);
+    const size_t smem1 = ((size_t)kSchurRB * 6 * kSchurTP + 2 * kSchurTP + (size_t)(kSchurRB * (kSchurRB + 1) / 2) * 42) * sizeof(float);
+    const size_t smem2 = ((size_t)2 * kSchurRB * 6 * kSchurTP + 2 * kSchurTP + (size_t)(kSchurRB * kSchurRB) * 42) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
-      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "schur smem attr");
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "schur smem attr");
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur smem attr");
       attr_set = true;
     }
-    ba_schur_kernel<<<g2, kSchurThreads, smem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
-                                                     WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
-                                                     WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
-    DBA_CHECK_LAUNCH("ba_schur");
+    ba_schur_kernel<true><<<g2, kSchurThreads, smem1, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                           WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
+                                                           WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+    DBA_CHECK_LAUNCH("ba_schur<single>");
+    ba_schur_kernel<false><<<g2, kSchurThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
+                                                            WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+    DBA_CHECK_LAUNCH("ba_schur<multi>");
   }
   return DBA_OK;
 }
@@ -900,8 +771,10 @@ extern "C" int dba_ba_solve(const dba_ba_args* a) {
   double* Hsys = WS(double, L.off_sys);
   double* bsys = Hsys + (size_t)L.n * L.n;
   float* dx = WS(float, L.off_dx);
-  ba_solve_kernel<<<1, kSolveThreads, 0, st>>>(Hsys, bsys, WS(double, L.off_L), L.n, a->lm, a->ep, WS(int, L.off_hdr), dx);
-  DBA_CHECK_LAUNCH("ba_solve");
+  {
+    int rc2 = chol_solve_launch(Hsys, bsys, L.n, (double)a->lm, (double)a->ep, WS(void, L.off_L), WS(int, L.off_hdr) + HDR_CHOL_FAIL, dx, st);
+    if (rc2) return rc2;
+  }
   if (!a->motion_only) {
     DBA_CHECK_ARG(a->dz_out != nullptr, "dz_out missing");
     dim3 grid((HW + 255) / 256, a->n_frames);
@@ -910,7 +783,7 @@ extern "C" int dba_ba_solve(const dba_ba_args* a) {
                                             WS(float, L.off_Ei), dx, a->disps, a->dz_out, a->own_lo, a->own_hi);
     DBA_CHECK_LAUNCH("ba_backsub");
   }
-  ba_pose_retr_kernel<<<(L.P + 127) / 128, 128, 0, st>>>(a->poses, dx, a->t0, L.P, a->dx_out);
+  ba_pose_retr_kernel<<<(L.P + 127) / 128, 128, 0, st>>>(a->poses, dx, a->t0, L.P, a->dx_out, WS(int, L.off_hdr));
   DBA_CHECK_LAUNCH("ba_pose_retr");
   return DBA_OK;
 }

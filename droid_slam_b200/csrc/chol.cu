@@ -1,0 +1,284 @@
+// Damped SPD solve of the reduced pose system on the device, fp64:  (H + diag(ep + lm*diag(H))) x = b.
+//
+// Replaces the reference's host-side SparseBlock::solve (src/droid_kernels.cu:1201-1222: Eigen::SimplicialLLT in
+// fp64 on the CPU behind two PCIe round trips).  Same contract: fp64 arithmetic, a non-positive pivot means
+// "not SPD" and yields x = 0.
+//
+// One thread-block CLUSTER (up to 16 CTAs, i.e. up to 16 SMs of one GPC) runs a right-looking tiled Cholesky with
+// 32x32 fp64 tiles that live in global memory (L2 resident: 6P x 6P doubles is 1.5 MB for P = 71).  Per panel k:
+//     TRSM of the column-k tiles (one warp per tile, lane = row, forward substitution against L_kk in shared memory)
+//       -- cluster barrier --
+//     trailing update A_ij -= L_ik L_jk^T (one warp per tile, L_jk staged in the warp's shared-memory slab); the warp that
+//     owns tile (k+1,k+1) factors it right away (warp-level potrf in registers, shuffles only) while the other warps
+//     are still updating; a spare warp inverts L_kk for the backward pass
+//       -- cluster barrier --
+// i.e. two hardware cluster barriers per panel instead of kernel launches or grid-wide syncs.
+// The right-hand side rides along as an extra tile row, so L^-1 b comes out of the factorisation for free; the
+// backward substitution uses the inverted diagonal tiles and runs in CTA 0.
+#include "common.cuh"
+#include <cooperative_groups.h>
+#include <math.h>
+
+namespace cg = cooperative_groups;
+
+namespace dba {
+
+constexpr int kT = 32;                 // tile edge
+constexpr int kCholThreads = 256;      // 8 warps per CTA
+constexpr int kCholWarps = kCholThreads / 32;
+
+__device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ void stcg(double* p, double v) { __stcg(p, v); }
+
+// Cholesky of a 32x32 tile, one row per lane, in registers.  Returns false on a non-positive pivot.
+__device__ __forceinline__ bool warp_potrf(double (&a)[kT], int lane) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < kT; k++) {
+    const double d = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(d > 0.0)) ok = false;
+    const double r = rsqrt(d);
+    const double l_kk = d * r;
+    const double l = (lane == k) ? l_kk : a[k] * r;
+    a[k] = l;
+#pragma unroll
+    for (int j = k + 1; j < kT; j++) {
+      const double ljk = __shfl_sync(0xffffffffu, l, j);
+      a[j] -= l * ljk;   // only rows >= j are meaningful
+    }
+  }
+  return ok;
+}
+
+struct CholParams {
+  const double* H;   // [n][n] full symmetric (only the lower triangle is read)
+  const double* b;   // [n]
+  double* L;         // [(nt+1)*32][nt*32] row-major working matrix (tile row nt carries b^T in its row 0)
+  double* Linv;      // [nt][32][32] inverses of the diagonal tiles
+  int* fail;         // sticky flag: non-positive pivot
+  float* x;          // [n] result (fp32 like the reference's dx)
+  int n, nt;
+  double lm, ep;
+};
+
+__global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ncta = (int)cluster.num_blocks();
+  const int cta = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gw = cta * kCholWarps + warp;          // warp id within the cluster
+  const int nwarps = ncta * kCholWarps;
+  const int nt = p.nt, n = p.n;
+  const int ld = nt * kT;                          // leading dimension of L
+  double* __restrict__ L = p.L;
+
+  __shared__ double s_Lkk[kT][kT + 1];
+  __shared__ double s_rdiag[kT];
+  extern __shared__ double s_dyn[];                  // per-warp slabs [kCholWarps][kT][kT]: L_jk of the tile update
+  double (*s_B)[kT][kT] = reinterpret_cast<double (*)[kT][kT]>(s_dyn);
+  __shared__ double s_vec[kT];
+
+  // ---- load: lower tiles of H with damping (reference :1205-1206), identity padding, rhs row ------------------
+  {
+    const size_t total = (size_t)(nt + 1) * kT * ld;
+    for (size_t idx = (size_t)cta * kCholThreads + tid; idx < total; idx += (size_t)ncta * kCholThreads) {
+      const int r = (int)(idx / ld), c = (int)(idx - (size_t)r * ld);
+      double v = 0.0;
+      if (r < nt * kT) {
+        if (r < n && c < n) {
+          if (c <= r) { v = p.H[(size_t)r * n + c]; if (r == c) v += p.ep + p.lm * v; }
+        } else if (r == c) v = 1.0;
+      } else if (r == nt * kT && c < n) v = p.b[c];
+      stcg(L + idx, v);
+    }
+  }
+  if (cta == 0 && tid == 0) *p.fail = 0;
+  cluster.sync();
+
+  // ---- potrf of tile (0,0) --------------------------------------------------------------------------------------
+  if (gw == 0) {
+    double a[kT];
+#pragma unroll
+    for (int c = 0; c < kT; c++) a[c] = ldcg(L + (size_t)lane * ld + c);
+    if (!warp_potrf(a, lane) && lane == 0) *p.fail = 1;
+#pragma unroll
+    for (int c = 0; c < kT; c++) stcg(L + (size_t)lane * ld + c, (c <= lane) ? a[c] : 0.0);
+  }
+  cluster.sync();
+
+  for (int k = 0; k < nt; k++) {
+    // ---- every CTA: L_kk and its reciprocal diagonal into shared memory
+    for (int e = tid; e < kT * kT; e += kCholThreads) {
+      const int r = e >> 5, c = e & 31;
+      const double v = ldcg(L + (size_t)(k * kT + r) * ld + k * kT + c);
+      s_Lkk[r][c] = v;
+      if (r == c) s_rdiag[r] = 1.0 / v;
+    }
+    __syncthreads();
+    // ---- TRSM: tiles (i,k), i = k+1 .. nt (tile row nt is the right-hand side)
+    for (int i = k + 1 + gw; i <= nt; i += nwarps) {
+      double a[kT];
+      double* rowp = L + (size_t)(i * kT + lane) * ld + k * kT;
+#pragma unroll
+      for (int c = 0; c < kT; c++) a[c] = ldcg(rowp + c);
+#pragma unroll
+      for (int c = 0; c < kT; c++) {
+        const double xv = a[c] * s_rdiag[c];
+        a[c] = xv;
+#pragma unroll
+        for (int j = c + 1; j < kT; j++) a[j] -= xv * s_Lkk[j][c];
+        asm volatile("" ::: "memory");
+      }
+#pragma unroll
+      for (int c = 0; c < kT; c++) stcg(rowp + c, a[c]);
+    }
+    cluster.sync();
+    // ---- trailing update with panel k; potrf of the next diagonal tile; inverse of L_kk
+    const int rem = nt - k - 1;                       // remaining tile columns
+    const int ntri = rem * (rem + 1) / 2;
+    const int ntasks = ntri + rem;                    // tiles (i,j), k<j<=i<nt, plus the rhs row tiles (nt,j)
+    // task 0 is tile (k+1,k+1) so that its owner starts the next potrf as early as possible
+    for (int t = gw; t < ntasks; t += nwarps) {
+      int i, j;
+      if (t < ntri) {
+        int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while (bi * (bi + 1) / 2 > t) bi--;
+        while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+        const int bj = t - bi * (bi + 1) / 2;
+        i = k + 1 + bi; j = k + 1 + bj;
+      } else { i = nt; j = k + 1 + (t - ntri); }
+      // stage L_jk into this warp's slab (coalesced rows)
+#pragma unroll 4
+      for (int r = 0; r < kT; r++) s_B[warp][r][lane] = ldcg(L + (size_t)(j * kT + r) * ld + k * kT + lane);
+      double lik[kT];
+      const double* lrow = L + (size_t)(i * kT + lane) * ld + k * kT;
+#pragma unroll
+      for (int c = 0; c < kT; c++) lik[c] = ldcg(lrow + c);
+      __syncwarp();
+      double* crow = L + (size_t)(i * kT + lane) * ld + j * kT;
+      double cacc[kT];
+#pragma unroll
+      for (int c = 0; c < kT; c++) cacc[c] = ldcg(crow + c);
+#pragma unroll
+      for (int c = 0; c < kT; c++) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < kT; q++) s += lik[q] * s_B[warp][c][q];
+        cacc[c] -= s;
+        asm volatile("" ::: "memory");
+      }
+      __syncwarp();
+      if (i == j && i == k + 1) {      // next diagonal tile: factor it now
+        if (!warp_potrf(cacc, lane) && lane == 0) *p.fail = 1;
+#pragma unroll
+        for (int c = 0; c < kT; c++) stcg(crow + c, (c <= lane) ? cacc[c] : 0.0);
+      } else {
+#pragma unroll
+        for (int c = 0; c < kT; c++) stcg(crow + c, cacc[c]);
+      }
+    }
+    // inverse of L_kk (for the backward substitution) by the last warp of the cluster: lane j owns column j
+    if (gw == nwarps - 1) {
+      double xcol[kT];
+#pragma unroll
+      for (int i = 0; i < kT; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < i; m++) s += (m >= lane) ? s_Lkk[i][m] * xcol[m] : 0.0;
+        xcol[i] = (i == lane) ? s_rdiag[i] : ((i > lane) ? -s * s_rdiag[i] : 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
+    }
+    cluster.sync();
+  }
+
+  if (cta != 0) return;
+  // ---- backward substitution  L^T x = y  in CTA 0;  y^T = row 0 of tile row nt -------------------------------------
+  double* y = L + (size_t)(nt * kT) * ld;            // [ld], overwritten by x
+  for (int k = nt - 1; k >= 0; k--) {
+    if (warp == 0) {
+      // x_k = Linv_kk^T y_k : lane c computes sum_r Linv[r][c] * y[r]
+      const double yk = ldcg(y + k * kT + lane);
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < kT; r++) s += ldcg(p.Linv + ((size_t)k * kT + r) * kT + lane) * __shfl_sync(0xffffffffu, yk, r);
+      stcg(y + k * kT + lane, s);
+      s_vec[lane] = s;
+    }
+    __syncthreads();
+    // y_i -= L_ki^T x_k  for i < k : lane = column of tile (k,i)
+    for (int i = warp; i < k; i += kCholWarps) {
+      double s = 0.0;
+#pragma unroll 8
+      for (int r = 0; r < kT; r++) s += ldcg(L + (size_t)(k * kT + r) * ld + i * kT + lane) * s_vec[r];
+      stcg(y + i * kT + lane, ldcg(y + i * kT + lane) - s);
+    }
+    __syncthreads();
+  }
+  const bool failed = (*reinterpret_cast<volatile int*>(p.fail)) != 0;
+  for (int i = tid; i < n; i += kCholThreads) {
+    const double v = ldcg(y + i);
+    p.x[i] = (failed || !isfinite(v)) ? 0.f : (float)v;      // reference: solver.info() != Success -> zeros
+  }
+}
+
+size_t chol_workspace_bytes(int n) {
+  const size_t nt = (size_t)(n + kT - 1) / kT;
+  const size_t ld = nt * kT;
+  return ((nt + 1) * kT * ld + nt * kT * kT) * sizeof(double) + 256;
+}
+
+// H [n][n] fp64, b [n] fp64 -> x [n] fp32; fail flag is a device int
+int chol_solve_launch(const double* H, const double* b, int n, double lm, double ep, void* workspace, int* fail, float* x, cudaStream_t st) {
+  if (n <= 0) return DBA_OK;
+  CholParams p;
+  p.H = H; p.b = b; p.n = n; p.nt = (n + kT - 1) / kT; p.lm = lm; p.ep = ep; p.fail = fail; p.x = x;
+  const size_t ld = (size_t)p.nt * kT;
+  p.L = reinterpret_cast<double*>(workspace);
+  p.Linv = p.L + (size_t)(p.nt + 1) * kT * ld;
+
+  const size_t dyn_smem = (size_t)kCholWarps * kT * kT * sizeof(double);
+  static int cluster_size = 0;
+  if (cluster_size == 0) {
+    cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    int best = 8;
+    for (int cs = 16; cs >= 8; cs -= 8) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kCholThreads); cfg.dynamicSmemBytes = dyn_smem;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, chol_cluster_kernel, &cfg) == cudaSuccess && nclusters >= 1) { best = cs; break; }
+    }
+    cudaGetLastError();
+    cluster_size = best;
+  }
+  // small systems do not need the whole cluster
+  int cs = cluster_size;
+  const int tiles_first_panel = p.nt * (p.nt + 1) / 2;
+  while (cs > 1 && (cs / 2) * kCholWarps >= tiles_first_panel) cs /= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kCholThreads); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  DBA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, p), "chol_cluster_kernel launch");
+  return DBA_OK;
+}
+
+}  // namespace dba
+
+// standalone entry (used by the solver tests and by callers that already hold a reduced system)
+extern "C" size_t dba_solve_workspace_bytes(int n) { return dba::chol_workspace_bytes(n) + 64; }
+
+extern "C" int dba_solve_spd(const double* H, const double* b, int n, float lm, float ep, float* x, int* fail_flag_device,
+                             void* workspace, size_t workspace_bytes, dba_stream_t stream) {
+  DBA_CHECK_ARG(n >= 0, "negative n");
+  if (n == 0) return DBA_OK;
+  DBA_CHECK_ARG(H && b && x && fail_flag_device && workspace, "null pointer");
+  if (workspace_bytes < dba::chol_workspace_bytes(n)) { dba::set_error("solve workspace too small"); return DBA_ERR_WORKSPACE; }
+  return dba::chol_solve_launch(H, b, n, (double)lm, (double)ep, workspace, fail_flag_device, x, (cudaStream_t)stream);
+}

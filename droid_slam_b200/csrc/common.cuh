@@ -10,6 +10,9 @@
 namespace dba {
 
 void set_error(const char* fmt, ...);
+// chol.cu: damped SPD solve (fp64, one thread-block cluster)
+size_t chol_workspace_bytes(int n);
+int chol_solve_launch(const double* H, const double* b, int n, double lm, double ep, void* workspace, int* fail, float* x, cudaStream_t st);
 int cuda_fail(cudaError_t e, const char* what);
 
 #define DBA_CHECK_ARG(cond, msg)                                   \

@@ -89,7 +89,7 @@ int dba_iproj(const float* poses, const float* disps, const float* intrinsics, f
  *
  * The call is split at the one point where a multi-GPU run exchanges data:
  *   dba_ba_prepare   graph bookkeeping (unique / CSR by source frame), once per call
- *   dba_ba_build     per-edge blocks + depth elimination -> reduced pose system  Hsys [6P,6P] f64 (full, symmetric),
+ *   dba_ba_build     per-edge blocks + depth elimination -> reduced pose system  Hsys [6P,6P] f64 (LOWER triangle valid),
  *                    bsys [6P] f64 (edge-sharded runs all-reduce exactly this buffer, 8*(36P^2+6P) bytes)
  *   dba_ba_solve     damping + Cholesky (fp64) -> dx, back-substitution -> dz, retraction of poses and disps
  * dba_ba runs prepare + iterations x (build, solve).
@@ -122,6 +122,14 @@ int dba_ba(const dba_ba_args* a, int iterations);
  * workspace and the sticky device status word (0 = ok, bit0 = index out of range, bit1 = eta rows != M,
  * bit2 = Cholesky hit a non-positive pivot in some iteration -> that iteration's dx = 0 like the reference). */
 int dba_ba_read_info(const dba_ba_args* a, int* n_depth_frames, int* device_status);
+
+/* ---- standalone damped SPD solve (the solver inside dba_ba_solve) ---------------------------------------
+ * (H + diag(ep + lm*diag(H))) x = b with H [n,n] fp64 (full symmetric), b [n] fp64 -> x [n] fp32, on the device in
+ * fp64; replaces SparseBlock::solve (reference src/droid_kernels.cu:1201-1222).  *fail_flag_device is set to 1 and x to 0
+ * when a pivot is not positive (reference: solver.info() != Eigen::Success). */
+size_t dba_solve_workspace_bytes(int n);
+int dba_solve_spd(const double* H, const double* b, int n, float lm, float ep, float* x, int* fail_flag_device,
+                  void* workspace, size_t workspace_bytes, dba_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -241,3 +241,27 @@ def test_ba_cholesky_failure_gives_zero_update(capi):
                             s["eta"].to(dev), s["ii"].to(dev), s["jj"].to(dev), s["t0"], s["t1"], 1, 0.0, -1e9, True, s["M"])
     assert st & 4
     assert float(dx.abs().max()) == 0.0 and torch.equal(P.cpu(), s["poses"])
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [6, 30, 42, 100, 426, 1000])
+def test_cluster_cholesky_solver_matches_fp64_lapack(capi, n):
+    """the standalone damped SPD solve (thread-block-cluster tiled Cholesky, fp64) against torch.linalg in fp64"""
+    g = torch.Generator().manual_seed(n)
+    A = torch.randn(n, n + 8, generator=g, dtype=torch.float64)
+    H = A @ A.t() + 1e-3 * torch.eye(n, dtype=torch.float64)                # SPD, condition number ~1e4-1e6
+    b = torch.randn(n, generator=g, dtype=torch.float64)
+    lm, ep = 1e-4, 0.1
+    lm32 = float(torch.tensor(lm, dtype=torch.float32)); ep32 = float(torch.tensor(ep, dtype=torch.float32))
+    Hd = H.clone(); Hd.diagonal().add_(ep32 + lm32 * H.diagonal())
+    ref = torch.linalg.solve(Hd, b)
+    ws = torch.empty(capi.dba_solve_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    x = torch.full((n,), float("nan"), device=dev)
+    fail = torch.full((1,), 7, dtype=torch.int32, device=dev)
+    c_api.check(capi.dba_solve_spd(ptr(H.to(dev)), ptr(b.to(dev)), n, lm, ep, ptr(x), ptr(fail), ptr(ws), ws.numel(), stream()), "solve_spd")
+    assert int(fail) == 0
+    assert rel_err(x, ref, floor=float(ref.abs().max())) < 1e-6          # fp32 output of an fp64 solve
+    # not SPD -> zeros and the flag
+    Hbad = H.clone(); Hbad[n // 2, n // 2] = -5.0
+    c_api.check(capi.dba_solve_spd(ptr(Hbad.to(dev)), ptr(b.to(dev)), n, 0.0, 0.0, ptr(x), ptr(fail), ptr(ws), ws.numel(), stream()), "solve_spd")
+    assert int(fail) == 1 and float(x.abs().max()) == 0.0
