@@ -5,7 +5,7 @@ import os
 _LIB = None
 
 SYMBOLS = [
-    "dba_last_error", "dba_version",
+    "dba_last_error", "dba_version", "dba_set_l2_fetch_granularity", "dba_get_l2_fetch_granularity",
     "dba_corr_index_forward", "dba_corr_index_backward", "dba_altcorr_forward", "dba_altcorr_backward",
     "dba_projmap", "dba_frame_distance", "dba_depth_filter", "dba_iproj",
     "dba_ba_workspace_bytes", "dba_ba_system_offset", "dba_ba_system_bytes",

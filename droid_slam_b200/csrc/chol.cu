@@ -30,6 +30,17 @@ constexpr int kCholWarps = kCholThreads / 32;
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ void stcg(double* p, double v) { __stcg(p, v); }
 
+// 1/sqrt(d) in fp64 from the fp32 MUFU approximation and two Newton steps (the library rsqrt(double) is a long
+// software sequence sitting on the critical path of every pivot)
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+  double r = (double)rsqrtf((float)d);
+  const double hd = 0.5 * d;
+  r = r * (1.5 - hd * r * r);
+  r = r * (1.5 - hd * r * r);
+  return r;
+}
+
 // Cholesky of a 32x32 tile, one row per lane, in registers.  Returns false on a non-positive pivot.
 __device__ __forceinline__ bool warp_potrf(double (&a)[kT], int lane) {
   bool ok = true;
@@ -37,7 +48,7 @@ __device__ __forceinline__ bool warp_potrf(double (&a)[kT], int lane) {
   for (int k = 0; k < kT; k++) {
     const double d = __shfl_sync(0xffffffffu, a[k], k);
     if (!(d > 0.0)) ok = false;
-    const double r = rsqrt(d);
+    const double r = fast_rsqrt(d);
     const double l_kk = d * r;
     const double l = (lane == k) ? l_kk : a[k] * r;
     a[k] = l;
@@ -74,8 +85,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
 
   __shared__ double s_Lkk[kT][kT + 1];
   __shared__ double s_rdiag[kT];
-  extern __shared__ double s_dyn[];                  // per-warp slabs [kCholWarps][kT][kT]: L_jk of the tile update
-  double (*s_B)[kT][kT] = reinterpret_cast<double (*)[kT][kT]>(s_dyn);
+  extern __shared__ double s_dyn[];                  // per-warp slabs, rows padded to 33 doubles
+  double (*s_A)[kT][kT + 1] = reinterpret_cast<double (*)[kT][kT + 1]>(s_dyn);
+  double (*s_B)[kT][kT + 1] = reinterpret_cast<double (*)[kT][kT + 1]>(s_dyn + (size_t)kCholWarps * kT * (kT + 1));
   __shared__ double s_vec[kT];
 
   // ---- load: lower tiles of H with damping (reference :1205-1206), identity padding, rhs row ------------------
@@ -87,6 +99,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       if (r < nt * kT) {
         if (r < n && c < n) {
           if (c <= r) { v = p.H[(size_t)r * n + c]; if (r == c) v += p.ep + p.lm * v; }
+          else if ((r >> 5) == (c >> 5)) v = p.H[(size_t)c * n + r];     // diagonal tiles are kept fully symmetric
         } else if (r == c) v = 1.0;
       } else if (r == nt * kT && c < n) v = p.b[c];
       stcg(L + idx, v);
@@ -118,9 +131,12 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     // ---- TRSM: tiles (i,k), i = k+1 .. nt (tile row nt is the right-hand side)
     for (int i = k + 1 + gw; i <= nt; i += nwarps) {
       double a[kT];
-      double* rowp = L + (size_t)(i * kT + lane) * ld + k * kT;
+      double* tile = L + (size_t)(i * kT) * ld + k * kT;
+#pragma unroll 8
+      for (int r = 0; r < kT; r++) s_A[warp][r][lane] = ldcg(tile + (size_t)r * ld + lane);     // coalesced rows
+      __syncwarp();
 #pragma unroll
-      for (int c = 0; c < kT; c++) a[c] = ldcg(rowp + c);
+      for (int c = 0; c < kT; c++) a[c] = s_A[warp][lane][c];                                   // lane = row
 #pragma unroll
       for (int c = 0; c < kT; c++) {
         const double xv = a[c] * s_rdiag[c];
@@ -129,8 +145,13 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
         for (int j = c + 1; j < kT; j++) a[j] -= xv * s_Lkk[j][c];
         asm volatile("" ::: "memory");
       }
+      __syncwarp();
 #pragma unroll
-      for (int c = 0; c < kT; c++) stcg(rowp + c, a[c]);
+      for (int c = 0; c < kT; c++) s_A[warp][lane][c] = a[c];
+      __syncwarp();
+#pragma unroll 8
+      for (int r = 0; r < kT; r++) stcg(tile + (size_t)r * ld + lane, s_A[warp][r][lane]);
+      __syncwarp();
     }
     cluster.sync();
     // ---- trailing update with panel k; potrf of the next diagonal tile; inverse of L_kk
@@ -147,35 +168,36 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
         const int bj = t - bi * (bi + 1) / 2;
         i = k + 1 + bi; j = k + 1 + bj;
       } else { i = nt; j = k + 1 + (t - ntri); }
-      // stage L_jk into this warp's slab (coalesced rows)
-#pragma unroll 4
-      for (int r = 0; r < kT; r++) s_B[warp][r][lane] = ldcg(L + (size_t)(j * kT + r) * ld + k * kT + lane);
-      double lik[kT];
-      const double* lrow = L + (size_t)(i * kT + lane) * ld + k * kT;
-#pragma unroll
-      for (int c = 0; c < kT; c++) lik[c] = ldcg(lrow + c);
-      __syncwarp();
-      double* crow = L + (size_t)(i * kT + lane) * ld + j * kT;
+      // C_ij -= L_ik L_jk^T with lane = column c of C:  C[r][c] -= sum_q A[r][q] * B[c][q]
+      const double* At = L + (size_t)(i * kT) * ld + k * kT;
+      const double* Bt = L + (size_t)(j * kT) * ld + k * kT;
+      double* Ct = L + (size_t)(i * kT) * ld + j * kT;
+#pragma unroll 8
+      for (int r = 0; r < kT; r++) { s_A[warp][r][lane] = ldcg(At + (size_t)r * ld + lane); s_B[warp][r][lane] = ldcg(Bt + (size_t)r * ld + lane); }
       double cacc[kT];
 #pragma unroll
-      for (int c = 0; c < kT; c++) cacc[c] = ldcg(crow + c);
+      for (int r = 0; r < kT; r++) cacc[r] = ldcg(Ct + (size_t)r * ld + lane);                  // coalesced: row r, column lane
+      __syncwarp();
+#pragma unroll 4
+      for (int q = 0; q < kT; q++) {
+        const double bq = s_B[warp][lane][q];
 #pragma unroll
-      for (int c = 0; c < kT; c++) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < kT; q++) s += lik[q] * s_B[warp][c][q];
-        cacc[c] -= s;
-        asm volatile("" ::: "memory");
+        for (int r = 0; r < kT; r++) cacc[r] -= s_A[warp][r][q] * bq;                          // broadcast read, 32 independent chains
       }
       __syncwarp();
-      if (i == j && i == k + 1) {      // next diagonal tile: factor it now
+      if (i == j && i == k + 1) {
+        // next diagonal tile: symmetric, so cacc[r] = C[r][lane] = C[lane][r] is ALSO row `lane`: factor it now
         if (!warp_potrf(cacc, lane) && lane == 0) *p.fail = 1;
 #pragma unroll
-        for (int c = 0; c < kT; c++) stcg(crow + c, (c <= lane) ? cacc[c] : 0.0);
+        for (int c = 0; c < kT; c++) s_A[warp][lane][c] = (c <= lane) ? cacc[c] : 0.0;
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < kT; r++) stcg(Ct + (size_t)r * ld + lane, s_A[warp][r][lane]);
       } else {
 #pragma unroll
-        for (int c = 0; c < kT; c++) stcg(crow + c, cacc[c]);
+        for (int r = 0; r < kT; r++) stcg(Ct + (size_t)r * ld + lane, cacc[r]);
       }
+      __syncwarp();
     }
     // inverse of L_kk (for the backward substitution) by the last warp of the cluster: lane j owns column j
     if (gw == nwarps - 1) {
@@ -238,7 +260,7 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   p.L = reinterpret_cast<double*>(workspace);
   p.Linv = p.L + (size_t)(p.nt + 1) * kT * ld;
 
-  const size_t dyn_smem = (size_t)kCholWarps * kT * kT * sizeof(double);
+  const size_t dyn_smem = (size_t)2 * kCholWarps * kT * (kT + 1) * sizeof(double);
   static int cluster_size = 0;
   if (cluster_size == 0) {
     cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);

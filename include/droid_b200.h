@@ -35,6 +35,9 @@ enum {
 };
 
 const char* dba_last_error(void);   /* thread-local, human readable */
+/* device-wide L2 fetch granularity hint (32/64/128 B; cudaLimitMaxL2FetchGranularity); -1 when it cannot be read */
+int dba_set_l2_fetch_granularity(int bytes);
+int dba_get_l2_fetch_granularity(void);
 int dba_version(void);              /* 100 * major + minor */
 
 /* ---- correlation volume lookup ------------------------------------------------------------------

@@ -258,10 +258,12 @@ def test_cluster_cholesky_solver_matches_fp64_lapack(capi, n):
     ws = torch.empty(capi.dba_solve_workspace_bytes(n), dtype=torch.uint8, device=dev)
     x = torch.full((n,), float("nan"), device=dev)
     fail = torch.full((1,), 7, dtype=torch.int32, device=dev)
-    c_api.check(capi.dba_solve_spd(ptr(H.to(dev)), ptr(b.to(dev)), n, lm, ep, ptr(x), ptr(fail), ptr(ws), ws.numel(), stream()), "solve_spd")
+    Hd_, bd_ = H.to(dev), b.to(dev)          # keep the device tensors alive across the asynchronous call
+    c_api.check(capi.dba_solve_spd(ptr(Hd_), ptr(bd_), n, lm, ep, ptr(x), ptr(fail), ptr(ws), ws.numel(), stream()), "solve_spd")
     assert int(fail) == 0
     assert rel_err(x, ref, floor=float(ref.abs().max())) < 1e-6          # fp32 output of an fp64 solve
     # not SPD -> zeros and the flag
     Hbad = H.clone(); Hbad[n // 2, n // 2] = -5.0
-    c_api.check(capi.dba_solve_spd(ptr(Hbad.to(dev)), ptr(b.to(dev)), n, 0.0, 0.0, ptr(x), ptr(fail), ptr(ws), ws.numel(), stream()), "solve_spd")
+    Hbad_ = Hbad.to(dev)
+    c_api.check(capi.dba_solve_spd(ptr(Hbad_), ptr(bd_), n, 0.0, 0.0, ptr(x), ptr(fail), ptr(ws), ws.numel(), stream()), "solve_spd")
     assert int(fail) == 1 and float(x.abs().max()) == 0.0
