@@ -8,69 +8,115 @@
 // 32x32 fp64 tiles that live in global memory (L2 resident: 6P x 6P doubles is 1.5 MB for P = 71).  Per panel k:
 //     TRSM of the column-k tiles (one warp per tile, lane = row, forward substitution against L_kk in shared memory)
 //       -- cluster barrier --
-//     trailing update A_ij -= L_ik L_jk^T (one warp per tile, L_jk staged in the warp's shared-memory slab); the warp that
-//     owns tile (k+1,k+1) factors it right away (warp-level potrf in registers, shuffles only) while the other warps
-//     are still updating; a spare warp inverts L_kk for the backward pass
+//     trailing update A_ij -= L_ik L_jk^T: one warp per tile with an 8x4 register block per lane (operands staged in the
+//     warp's padded shared-memory slabs, coalesced global I/O).  The NEXT diagonal tile is on the critical path, so CTA 0
+//     updates it with all 256 threads and its warp 0 factors it immediately (rows in registers, the pivot column is
+//     broadcast through shared memory) while every other warp of the cluster works on the remaining tiles; a spare
+//     warp inverts L_kk for the backward pass
 //       -- cluster barrier --
 // i.e. two hardware cluster barriers per panel instead of kernel launches or grid-wide syncs.
 // The right-hand side rides along as an extra tile row, so L^-1 b comes out of the factorisation for free; the
 // backward substitution uses the inverted diagonal tiles and runs in CTA 0.
+// (B200 note, measured: a dependent fp64 op costs ~10-20 cycles and a 64-bit warp shuffle pair is slower than a
+//  shared-memory broadcast, which is why the pivot column goes through shared memory and the pivot uses an fp32
+//  rsqrt seed + one Newton step -- 3e-14 relative, far below the fp32 rounding of the result.)
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace cg = cooperative_groups;
 
 namespace dba {
 
 constexpr int kT = 32;                 // tile edge
+constexpr int kTP = kT + 1;            // padded row length in shared memory
 constexpr int kCholThreads = 256;      // 8 warps per CTA
 constexpr int kCholWarps = kCholThreads / 32;
 
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CHOL_STAMP(slot) do { if (p.timing && cta == 0 && tid == 0) p.timing[(slot)] = gtimer(); } while (0)
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ void stcg(double* p, double v) { __stcg(p, v); }
 
-// 1/sqrt(d) in fp64 from the fp32 MUFU approximation and two Newton steps (the library rsqrt(double) is a long
-// software sequence sitting on the critical path of every pivot)
+// 1/sqrt(d): fp32 MUFU seed + one Newton step in fp64 (relative error ~3e-14)
 __device__ __forceinline__ double fast_rsqrt(double d) {
   if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
   double r = (double)rsqrtf((float)d);
-  const double hd = 0.5 * d;
-  r = r * (1.5 - hd * r * r);
-  r = r * (1.5 - hd * r * r);
+  r = r * (1.5 - (0.5 * d) * r * r);
   return r;
 }
 
-// Cholesky of a 32x32 tile, one row per lane, in registers.  Returns false on a non-positive pivot.
-__device__ __forceinline__ bool warp_potrf(double (&a)[kT], int lane) {
+// Cholesky of a 32x32 tile, one row per lane in registers; the pivot column is broadcast through `col` (2 x 32 doubles
+// of shared memory private to the warp).  rdiag_out receives 1/L[k][k] (lane k's value).  Returns false on a
+// non-positive pivot.
+__device__ __forceinline__ bool warp_potrf(double (&a)[kT], int lane, double* col, double& rdiag_out) {
   bool ok = true;
+  rdiag_out = 0.0;
 #pragma unroll
   for (int k = 0; k < kT; k++) {
     const double d = __shfl_sync(0xffffffffu, a[k], k);
     if (!(d > 0.0)) ok = false;
     const double r = fast_rsqrt(d);
-    const double l_kk = d * r;
-    const double l = (lane == k) ? l_kk : a[k] * r;
+    const double l = (lane == k) ? d * r : a[k] * r;
+    if (lane == k) rdiag_out = r;
     a[k] = l;
+    double* cb = col + (k & 1) * kT;
+    cb[lane] = l;
+    __syncwarp();
 #pragma unroll
-    for (int j = k + 1; j < kT; j++) {
-      const double ljk = __shfl_sync(0xffffffffu, l, j);
-      a[j] -= l * ljk;   // only rows >= j are meaningful
-    }
+    for (int j = k + 1; j < kT; j++) a[j] -= l * cb[j];   // only rows >= j are meaningful
   }
   return ok;
 }
 
 struct CholParams {
-  const double* H;   // [n][n] full symmetric (only the lower triangle is read)
+  const double* H;   // [n][n] fp64, lower triangle valid
   const double* b;   // [n]
   double* L;         // [(nt+1)*32][nt*32] row-major working matrix (tile row nt carries b^T in its row 0)
   double* Linv;      // [nt][32][32] inverses of the diagonal tiles
+  double* rdiag;     // [nt*32] reciprocals of diag(L)
   int* fail;         // sticky flag: non-positive pivot
   float* x;          // [n] result (fp32 like the reference's dx)
   int n, nt;
   double lm, ep;
+  unsigned long long* timing;   // debug (DBA_CHOL_TIMING=1): globaltimer stamps of CTA 0 / the potrf warp, else nullptr
 };
+
+// one warp: C (32x32 at Ct) -= A (at At) * B^T (at Bt); lane (rg = lane>>3, cg = lane&7) owns rows 8rg..8rg+7, cols 4cg..4cg+3
+__device__ __forceinline__ void warp_tile_update(const double* At, const double* Bt, double* Ct, int ld, int lane,
+                                                 double (*sA)[kTP], double (*sB)[kTP]) {
+#pragma unroll 8
+  for (int r = 0; r < kT; r++) { sA[r][lane] = ldcg(At + (size_t)r * ld + lane); sB[r][lane] = ldcg(Bt + (size_t)r * ld + lane); }
+  const int rg = lane >> 3, cgp = lane & 7;
+  double acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const double2 c01 = __ldcg(reinterpret_cast<const double2*>(Ct + (size_t)(8 * rg + i) * ld + 4 * cgp));
+    const double2 c23 = __ldcg(reinterpret_cast<const double2*>(Ct + (size_t)(8 * rg + i) * ld + 4 * cgp + 2));
+    acc[i][0] = c01.x; acc[i][1] = c01.y; acc[i][2] = c23.x; acc[i][3] = c23.y;
+  }
+  __syncwarp();
+#pragma unroll 4
+  for (int q = 0; q < kT; q++) {
+    double av[8], bv[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) av[i] = sA[8 * rg + i][q];
+#pragma unroll
+    for (int jx = 0; jx < 4; jx++) bv[jx] = sB[4 * cgp + jx][q];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int jx = 0; jx < 4; jx++) acc[i][jx] -= av[i] * bv[jx];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    __stcg(reinterpret_cast<double2*>(Ct + (size_t)(8 * rg + i) * ld + 4 * cgp), make_double2(acc[i][0], acc[i][1]));
+    __stcg(reinterpret_cast<double2*>(Ct + (size_t)(8 * rg + i) * ld + 4 * cgp + 2), make_double2(acc[i][2], acc[i][3]));
+  }
+  __syncwarp();
+}
 
 __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParams p) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -83,12 +129,15 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
   const int ld = nt * kT;                          // leading dimension of L
   double* __restrict__ L = p.L;
 
-  __shared__ double s_Lkk[kT][kT + 1];
+  __shared__ double s_Lkk[kT][kTP];
   __shared__ double s_rdiag[kT];
-  extern __shared__ double s_dyn[];                  // per-warp slabs, rows padded to 33 doubles
-  double (*s_A)[kT][kT + 1] = reinterpret_cast<double (*)[kT][kT + 1]>(s_dyn);
-  double (*s_B)[kT][kT + 1] = reinterpret_cast<double (*)[kT][kT + 1]>(s_dyn + (size_t)kCholWarps * kT * (kT + 1));
   __shared__ double s_vec[kT];
+  __shared__ double s_col[2 * kT];
+  extern __shared__ double s_dyn[];                  // per-warp slabs + two CTA-wide tiles, rows padded to 33 doubles
+  double (*s_A)[kT][kTP] = reinterpret_cast<double (*)[kT][kTP]>(s_dyn);
+  double (*s_B)[kT][kTP] = reinterpret_cast<double (*)[kT][kTP]>(s_dyn + (size_t)kCholWarps * kT * kTP);
+  double (*s_D)[kTP] = reinterpret_cast<double (*)[kTP]>(s_dyn + (size_t)2 * kCholWarps * kT * kTP);
+  double (*s_T)[kTP] = reinterpret_cast<double (*)[kTP]>(s_dyn + (size_t)2 * kCholWarps * kT * kTP + kT * kTP);
 
   // ---- load: lower tiles of H with damping (reference :1205-1206), identity padding, rhs row ------------------
   {
@@ -106,28 +155,32 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     }
   }
   if (cta == 0 && tid == 0) *p.fail = 0;
+  CHOL_STAMP(0);
   cluster.sync();
+  CHOL_STAMP(1);
 
   // ---- potrf of tile (0,0) --------------------------------------------------------------------------------------
   if (gw == 0) {
-    double a[kT];
+    double a[kT], rd;
 #pragma unroll
     for (int c = 0; c < kT; c++) a[c] = ldcg(L + (size_t)lane * ld + c);
-    if (!warp_potrf(a, lane) && lane == 0) *p.fail = 1;
+    if (!warp_potrf(a, lane, s_col, rd) && lane == 0) *p.fail = 1;
 #pragma unroll
     for (int c = 0; c < kT; c++) stcg(L + (size_t)lane * ld + c, (c <= lane) ? a[c] : 0.0);
+    stcg(p.rdiag + lane, rd);
   }
   cluster.sync();
+  CHOL_STAMP(2);
 
   for (int k = 0; k < nt; k++) {
     // ---- every CTA: L_kk and its reciprocal diagonal into shared memory
     for (int e = tid; e < kT * kT; e += kCholThreads) {
       const int r = e >> 5, c = e & 31;
-      const double v = ldcg(L + (size_t)(k * kT + r) * ld + k * kT + c);
-      s_Lkk[r][c] = v;
-      if (r == c) s_rdiag[r] = 1.0 / v;
+      s_Lkk[r][c] = ldcg(L + (size_t)(k * kT + r) * ld + k * kT + c);
     }
+    if (tid < kT) s_rdiag[tid] = ldcg(p.rdiag + k * kT + tid);
     __syncthreads();
+    CHOL_STAMP(8 + 8 * k + 0);
     // ---- TRSM: tiles (i,k), i = k+1 .. nt (tile row nt is the right-hand side)
     for (int i = k + 1 + gw; i <= nt; i += nwarps) {
       double a[kT];
@@ -153,52 +206,69 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       for (int r = 0; r < kT; r++) stcg(tile + (size_t)r * ld + lane, s_A[warp][r][lane]);
       __syncwarp();
     }
+    CHOL_STAMP(8 + 8 * k + 1);
     cluster.sync();
-    // ---- trailing update with panel k; potrf of the next diagonal tile; inverse of L_kk
+    CHOL_STAMP(8 + 8 * k + 2);
+    // ---- trailing update with panel k
     const int rem = nt - k - 1;                       // remaining tile columns
     const int ntri = rem * (rem + 1) / 2;
     const int ntasks = ntri + rem;                    // tiles (i,j), k<j<=i<nt, plus the rhs row tiles (nt,j)
-    // task 0 is tile (k+1,k+1) so that its owner starts the next potrf as early as possible
-    for (int t = gw; t < ntasks; t += nwarps) {
-      int i, j;
-      if (t < ntri) {
-        int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while (bi * (bi + 1) / 2 > t) bi--;
-        while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
-        const int bj = t - bi * (bi + 1) / 2;
-        i = k + 1 + bi; j = k + 1 + bj;
-      } else { i = nt; j = k + 1 + (t - ntri); }
-      // C_ij -= L_ik L_jk^T with lane = column c of C:  C[r][c] -= sum_q A[r][q] * B[c][q]
-      const double* At = L + (size_t)(i * kT) * ld + k * kT;
-      const double* Bt = L + (size_t)(j * kT) * ld + k * kT;
-      double* Ct = L + (size_t)(i * kT) * ld + j * kT;
-#pragma unroll 8
-      for (int r = 0; r < kT; r++) { s_A[warp][r][lane] = ldcg(At + (size_t)r * ld + lane); s_B[warp][r][lane] = ldcg(Bt + (size_t)r * ld + lane); }
-      double cacc[kT];
-#pragma unroll
-      for (int r = 0; r < kT; r++) cacc[r] = ldcg(Ct + (size_t)r * ld + lane);                  // coalesced: row r, column lane
-      __syncwarp();
-#pragma unroll 4
-      for (int q = 0; q < kT; q++) {
-        const double bq = s_B[warp][lane][q];
-#pragma unroll
-        for (int r = 0; r < kT; r++) cacc[r] -= s_A[warp][r][q] * bq;                          // broadcast read, 32 independent chains
+    if (cta == 0 && rem >= 1) {
+      // next diagonal tile (task 0): all 256 threads update it, warp 0 factors it
+      const double* At = L + (size_t)((k + 1) * kT) * ld + k * kT;
+      double* Ct = L + (size_t)((k + 1) * kT) * ld + (k + 1) * kT;
+      for (int e = tid; e < kT * kT; e += kCholThreads) {
+        const int r = e >> 5, c = e & 31;
+        s_D[r][c] = ldcg(At + (size_t)r * ld + c);
+        s_T[r][c] = ldcg(Ct + (size_t)r * ld + c);
       }
-      __syncwarp();
-      if (i == j && i == k + 1) {
-        // next diagonal tile: symmetric, so cacc[r] = C[r][lane] = C[lane][r] is ALSO row `lane`: factor it now
-        if (!warp_potrf(cacc, lane) && lane == 0) *p.fail = 1;
+      __syncthreads();
+      {
+        const int r = tid >> 3, c0 = (tid & 7) * 4;
+        double acc[4] = {s_T[r][c0], s_T[r][c0 + 1], s_T[r][c0 + 2], s_T[r][c0 + 3]};
+#pragma unroll 8
+        for (int q = 0; q < kT; q++) {
+          const double ar = s_D[r][q];
 #pragma unroll
-        for (int c = 0; c < kT; c++) s_A[warp][lane][c] = (c <= lane) ? cacc[c] : 0.0;
+          for (int jx = 0; jx < 4; jx++) acc[jx] -= ar * s_D[c0 + jx][q];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int jx = 0; jx < 4; jx++) s_T[r][c0 + jx] = acc[jx];
+      }
+      __syncthreads();
+      if (warp == 0) {
+        if (p.timing && lane == 0) p.timing[8 + 8 * k + 5] = gtimer();
+        double a[kT], rd;
+#pragma unroll
+        for (int c = 0; c < kT; c++) a[c] = s_T[lane][c];
+        if (!warp_potrf(a, lane, s_col, rd) && lane == 0) *p.fail = 1;
+        if (p.timing && lane == 0) p.timing[8 + 8 * k + 6] = gtimer();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < kT; c++) s_T[lane][c] = (c <= lane) ? a[c] : 0.0;
         __syncwarp();
 #pragma unroll 8
-        for (int r = 0; r < kT; r++) stcg(Ct + (size_t)r * ld + lane, s_A[warp][r][lane]);
-      } else {
-#pragma unroll
-        for (int r = 0; r < kT; r++) stcg(Ct + (size_t)r * ld + lane, cacc[r]);
+        for (int r = 0; r < kT; r++) stcg(Ct + (size_t)r * ld + lane, s_T[r][lane]);
+        stcg(p.rdiag + (k + 1) * kT + lane, rd);
       }
-      __syncwarp();
     }
+    // remaining tiles: every warp of the cluster except the factoring one
+    if (gw != 0) {
+      for (int t = gw; t < ntasks; t += nwarps - 1) {      // tasks 1..ntasks-1 over workers 1..nwarps-1
+        int i, j;
+        if (t < ntri) {
+          int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+          while (bi * (bi + 1) / 2 > t) bi--;
+          while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+          const int bj = t - bi * (bi + 1) / 2;
+          i = k + 1 + bi; j = k + 1 + bj;
+        } else { i = nt; j = k + 1 + (t - ntri); }
+        warp_tile_update(L + (size_t)(i * kT) * ld + k * kT, L + (size_t)(j * kT) * ld + k * kT, L + (size_t)(i * kT) * ld + j * kT, ld, lane,
+                         s_A[warp], s_B[warp]);
+      }
+    }
+    CHOL_STAMP(8 + 8 * k + 3);
     // inverse of L_kk (for the backward substitution) by the last warp of the cluster: lane j owns column j
     if (gw == nwarps - 1) {
       double xcol[kT];
@@ -213,6 +283,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
     }
     cluster.sync();
+    CHOL_STAMP(8 + 8 * k + 4);
   }
 
   if (cta != 0) return;
@@ -238,6 +309,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     }
     __syncthreads();
   }
+  CHOL_STAMP(3);
   const bool failed = (*reinterpret_cast<volatile int*>(p.fail)) != 0;
   for (int i = tid; i < n; i += kCholThreads) {
     const double v = ldcg(y + i);
@@ -248,7 +320,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
 size_t chol_workspace_bytes(int n) {
   const size_t nt = (size_t)(n + kT - 1) / kT;
   const size_t ld = nt * kT;
-  return ((nt + 1) * kT * ld + nt * kT * kT) * sizeof(double) + 256;
+  return ((nt + 1) * kT * ld + nt * kT * kT + nt * kT) * sizeof(double) + 256;
 }
 
 // H [n][n] fp64, b [n] fp64 -> x [n] fp32; fail flag is a device int
@@ -259,8 +331,9 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   const size_t ld = (size_t)p.nt * kT;
   p.L = reinterpret_cast<double*>(workspace);
   p.Linv = p.L + (size_t)(p.nt + 1) * kT * ld;
+  p.rdiag = p.Linv + (size_t)p.nt * kT * kT;
 
-  const size_t dyn_smem = (size_t)2 * kCholWarps * kT * (kT + 1) * sizeof(double);
+  const size_t dyn_smem = ((size_t)2 * kCholWarps + 2) * kT * kTP * sizeof(double);
   static int cluster_size = 0;
   if (cluster_size == 0) {
     cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -280,14 +353,34 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   }
   // small systems do not need the whole cluster
   int cs = cluster_size;
-  const int tiles_first_panel = p.nt * (p.nt + 1) / 2;
-  while (cs > 1 && (cs / 2) * kCholWarps >= tiles_first_panel) cs /= 2;
+  const int tiles_first_panel = p.nt * (p.nt + 1) / 2 + 1;
+  while (cs > 1 && (cs / 2) * kCholWarps - 1 >= tiles_first_panel) cs /= 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs); cfg.blockDim = dim3(kCholThreads); cfg.dynamicSmemBytes = dyn_smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  static unsigned long long* tbuf = nullptr;
+  static const bool want_timing = getenv("DBA_CHOL_TIMING") != nullptr;
+  p.timing = nullptr;
+  if (want_timing) {
+    if (!tbuf) cudaMallocHost(&tbuf, 4096 * sizeof(unsigned long long));
+    memset(tbuf, 0, 4096 * sizeof(unsigned long long));
+    if (8 + 8 * p.nt < 4096) p.timing = tbuf;
+  }
   DBA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, p), "chol_cluster_kernel launch");
+  if (p.timing) {
+    cudaStreamSynchronize(st);
+    const unsigned long long t0 = tbuf[0];
+    fprintf(stderr, "[chol timing] n=%d nt=%d cluster=%d  load %.1f us, potrf0 %.1f us, total-to-backsub-end %.1f us\n", n, p.nt, cs, (tbuf[1] - t0) / 1e3,
+            (tbuf[2] - tbuf[1]) / 1e3, (tbuf[3] - t0) / 1e3);
+    for (int k = 0; k < p.nt; k++) {
+      const unsigned long long* q = tbuf + 8 + 8 * k;
+      fprintf(stderr, "  panel %2d: Lkk-load@%.1f trsm(cta0) %.1f  barrier %.1f  update(cta0 thread0) %.1f  inv+barrier %.1f | diag tile: coop-update %.1f potrf %.1f\n", k,
+              (q[0] - t0) / 1e3, (q[1] - q[0]) / 1e3, (q[2] - q[1]) / 1e3, (q[3] - q[2]) / 1e3, (q[4] - q[3]) / 1e3,
+              q[5] ? (q[5] - q[2]) / 1e3 : 0.0, q[6] ? (q[6] - q[5]) / 1e3 : 0.0);
+    }
+  }
   return DBA_OK;
 }
 
