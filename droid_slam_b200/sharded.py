@@ -97,6 +97,8 @@ class ShardedBA:
         """poses/disps are the full (replicated) state; targets/weights/ii/jj are this rank's edge shard.
         In place on poses (all ranks identical) and disps (owned frames; all frames after the final exchange)."""
         own = bounds[self.rank]
+        if exchange_disps and self.world > 1:
+            self._disps_before = disps.clone()
         self.engine.setup(poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj, t0, t1, lm, ep, own)
         self.allreduce_bytes = 0
         for _ in range(iterations):
@@ -106,7 +108,11 @@ class ShardedBA:
                 self.allreduce_bytes += system.numel() * system.element_size()
             self.engine.solve()
         if exchange_disps and self.world > 1:
-            for r, (lo, hi) in enumerate(bounds):
-                if hi > lo:
-                    dist.broadcast(disps[lo:hi], src=dist.get_global_rank(self.group, r) if self.group is not None else r, group=self.group)
+            # owners' inverse depths: ONE all-reduce of the owner-masked delta instead of one broadcast per rank
+            lo, hi = own
+            delta = torch.zeros_like(disps)
+            if hi > lo:
+                delta[lo:hi] = disps[lo:hi] - self._disps_before[lo:hi]
+            dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.group)
+            disps.copy_(self._disps_before + delta)
         return poses, disps
