@@ -97,12 +97,19 @@ def make_graph(E, N, stereo=False, seed=0, t0=1):
                     edges.append((i, j))
     edges = edges[:E] if len(edges) > E else edges
     have = set(edges)
-    tries = 0
-    while len(edges) < E and tries < 100 * E:
-        tries += 1
-        i = int(torch.randint(0, N, (1,), generator=g)); j = int(torch.randint(0, N, (1,), generator=g))
-        if abs(i - j) > 2 and (i, j) not in have:
-            have.add((i, j)); edges.append((i, j))
+    # loop closures between covisible frames: 2 < |i-j| <= span, the span grows only when the near pairs are exhausted
+    span = 12
+    while len(edges) < E:
+        cand = [(i, j) for i in range(N) for j in range(N) if 2 < abs(i - j) <= span and (i, j) not in have]
+        if not cand:
+            if span >= N:
+                break
+            span = min(N, span * 2)
+            continue
+        order = torch.randperm(len(cand), generator=g).tolist()
+        for k in order[:E - len(edges)]:
+            have.add(cand[k]); edges.append(cand[k])
+        span = min(N, span * 2)
     perm = torch.randperm(len(edges), generator=g)
     ii = torch.tensor([edges[k][0] for k in perm.tolist()], dtype=torch.long)
     jj = torch.tensor([edges[k][1] for k in perm.tolist()], dtype=torch.long)
@@ -124,10 +131,14 @@ def make_scene(cfg="metric", seed=0, rgbd=False, **over):
     ii, jj = make_graph(E, N, stereo=c.get("stereo", False), seed=seed)
     E = ii.shape[0]
     t0 = c.get("t0", 1); t1 = c.get("t1", N)
-    coords, _ = reproject(poses_gt, disps_gt, intr, ii, jj)
+    coords, z_true = reproject(poses_gt, disps_gt, intr, ii, jj)
     targets = coords + 0.5 * torch.randn(E, ht, wd, 2, generator=g, dtype=torch.float64)
     weights = torch.rand(E, ht, wd, 2, generator=g, dtype=torch.float64)
     weights = torch.where(torch.rand(E, ht, wd, 2, generator=g) < 0.1, torch.zeros_like(weights), weights)
+    # like the update operator, give no confidence to points that are not observable from the target frame
+    visible = (z_true > 0.5) & (coords[..., 0] > -wd) & (coords[..., 0] < 2 * wd) & (coords[..., 1] > -ht) & (coords[..., 1] < 2 * ht)
+    weights = weights * visible[..., None].to(weights.dtype)
+    targets = torch.where(visible[..., None], targets, torch.zeros_like(targets))
     kx = torch.unique(torch.cat([torch.arange(t0, t1), ii]))
     M = kx.shape[0]
     eta = 0.2 * 0.01 * F.softplus(torch.randn(M, ht, wd, generator=g, dtype=torch.float64)) + 1e-7

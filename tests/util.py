@@ -49,7 +49,7 @@ def c_ba(L, poses, disps, intr, disps_sens, targets, weights, eta, ii, jj, t0, t
     a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
     a.stream = torch.cuda.current_stream().cuda_stream
     a.own_lo, a.own_hi, a.eta_by_frame = 0, N, 0
-    c_api.check(L.dba_ba(ctypes.byref(a), itrs), "ba")
+    c_api.check(L.dba_ba(ctypes.byref(a), itrs) if itrs > 0 else L.dba_ba_prepare(ctypes.byref(a)), "ba")
     m = ctypes.c_int(0); st = ctypes.c_int(0)
     c_api.check(L.dba_ba_read_info(ctypes.byref(a), ctypes.byref(m), ctypes.byref(st)), "ba_read_info")
     return dx, dz, m.value, st.value, (a, ws)
