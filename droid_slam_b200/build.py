@@ -19,7 +19,7 @@ OBJDIR = os.path.join(PKG, "build")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CUDA_SOURCES = ["common.cu", "corr_index.cu", "altcorr.cu", "geom.cu", "ba.cu", "chol.cu"]
+CUDA_SOURCES = ["common.cu", "corr_index.cu", "altcorr.cu", "geom.cu", "ba.cu", "chol.cu", "corr_volume.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177"]
 

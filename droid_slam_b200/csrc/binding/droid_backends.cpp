@@ -214,6 +214,24 @@ std::vector<torch::Tensor> altcorr_backward(torch::Tensor fmap1, torch::Tensor f
   return {g1, g2};
 }
 
+// extension beyond the reference's nine callables: CorrBlock.__init__ in one tensor-core kernel
+// (reference droid_slam/modules/corr.py:24-38,63-71).  fmap1/fmap2 [N,128,ht,wd] f16, ii/jj [E] -> 4 pyramid levels.
+std::vector<torch::Tensor> corr_volume_pyramid(torch::Tensor fmap1, torch::Tensor fmap2, torch::Tensor ii, torch::Tensor jj) {
+  CHECK_INPUT(fmap1); CHECK_INPUT(fmap2); CHECK_INPUT(ii); CHECK_INPUT(jj); CHECK_I64(ii); CHECK_I64(jj);
+  TORCH_CHECK(fmap1.dim() == 4 && fmap2.dim() == 4, "fmaps must be [N,C,ht,wd]");
+  TORCH_CHECK(fmap1.scalar_type() == torch::kFloat16 && fmap2.scalar_type() == torch::kFloat16, "corr_volume_pyramid: float16 feature maps expected");
+  TORCH_CHECK(fmap1.size(1) == fmap2.size(1) && fmap1.size(2) == fmap2.size(2) && fmap1.size(3) == fmap2.size(3), "fmap shapes differ");
+  c10::cuda::CUDAGuard guard(fmap1.device());
+  const int E = (int)ii.size(0), C = (int)fmap1.size(1), ht = (int)fmap1.size(2), wd = (int)fmap1.size(3);
+  TORCH_CHECK(jj.size(0) == E, "ii and jj must have the same length");
+  std::vector<torch::Tensor> out;
+  for (int l = 0; l < 4; l++) out.push_back(torch::empty({E, ht, wd, ht >> l, wd >> l}, fmap1.options()));
+  check_status(dba_corr_volume_pyramid(fmap1.data_ptr(), fmap2.data_ptr(), ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), out[0].data_ptr(),
+                                       out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), E, (int)fmap1.size(0), (int)fmap2.size(0), C, ht, wd,
+                                       DBA_F16, cur_stream()), "corr_volume_pyramid");
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native droid_backends (drop-in for princeton-vl/DROID-SLAM src/droid.cpp)";
   // bundle adjustment kernels
@@ -227,5 +245,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("altcorr_backward", &altcorr_backward, "ALTCORR backward");
   m.def("corr_index_forward", &corr_index_forward, "INDEX forward");
   m.def("corr_index_backward", &corr_index_backward, "INDEX backward");
+  m.def("corr_volume_pyramid", &corr_volume_pyramid, "all-pairs correlation + 4-level pyramid (tcgen05), B200 extension");
   m.def("_b200_native", []() { return true; });
 }

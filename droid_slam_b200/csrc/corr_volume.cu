@@ -1,0 +1,311 @@
+// All-pairs correlation volume + 4-level pooled pyramid in ONE pass on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces CorrBlock.__init__ / CorrBlock.corr (reference droid_slam/modules/corr.py:24-38, 63-71): a cuBLAS batched GEMM
+// writing the [E,HW,HW] level-0 volume followed by three avg_pool2d passes that re-read it.  Here, per edge e:
+//     L0[m][n]  = fp16( (1/16) * sum_c f1[ii[e]][c][m] * f2[jj[e]][c][n] )           (fp32 accumulation in TMEM)
+//     L1..L3    = 2x2 average pooling over n = (y2,x2), each level from the fp16-rounded level below (like ATen)
+// are produced by one kernel: the GEMM is write bound (2*HW^2*128 flop vs 1.33*HW^2*2 bytes per edge, ~150 flop/B, far
+// below the B200 ridge), so the pyramid is computed in the epilogue from the accumulator while it is still on chip and the
+// volume is written exactly once (25.1 MB/edge at 48x64 instead of ~50 MB of traffic for GEMM + 3 pooling passes).
+//
+// CTA = (edge, 128 source pixels m).  Warp 0: TMA producer (cp.async.bulk.tensor, 128B swizzle) -- the A tile
+// [128 ch x 128 px] once, then B chunks [128 ch x 256 px] (= 4 image rows of frame j), double buffered.  Warp 1: MMA issuer,
+// tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16 x 8, both operands MN-major straight from the [C,H,W] feature
+// layout (no transposes anywhere), two 256-column fp32 accumulators in TMEM so the MMA of chunk c+1 overlaps the epilogue of
+// chunk c.  Warps 2-5: epilogue, tcgen05.ld 32 lanes x 32 columns, thread = one source pixel row m, which makes every
+// pooling window thread-local (registers only).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace dba {
+
+constexpr int kCvThreads = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kCvM = 128;                // source pixels per CTA
+constexpr int kCvN = 256;                // target pixels per chunk (4 image rows at wd = 64)
+constexpr int kCvK = 128;                // channels
+constexpr int kBoxBytes = 64 * kCvK * 2; // one TMA box: 64 pixels x 128 channels fp16 = 16 KB
+constexpr int kSmemA = 2 * kBoxBytes;    // 32 KB
+constexpr int kSmemB = 4 * kBoxBytes;    // 64 KB per stage
+constexpr int kCvSmem = kSmemA + 2 * kSmemB + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// shared-memory matrix descriptor, MN-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version 1 <<46 | layout_type 2 <<61.  LBO = byte distance between 64-element MN atoms, SBO = between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=f32, a=b=f16, both MN-major, N>>3 at bit 17, M>>4 at bit 24
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                 // c_format = F32
+  d |= 1u << 15;                // a_major = MN
+  d |= 1u << 16;                // b_major = MN
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+}
+
+struct CvParams {
+  const int64_t* ii; const int64_t* jj;
+  __half* out0; __half* out1; __half* out2; __half* out3;
+  int HW, wd, n_chunks;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_hh(__half lo, __half hi) { return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16); }
+// 2x2 average: `top` and `bot` are half2 words holding two horizontally adjacent values of two vertically adjacent rows;
+// fp32 accumulate, rounded to fp16 (ATen avg_pool2d on half tensors)
+__device__ __forceinline__ __half avg4w(uint32_t top, uint32_t bot) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&top));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&bot));
+  return __float2half_rn((a.x + a.y + b.x + b.y) * 0.25f);
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) corr_volume_pyramid_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                           const __grid_constant__ CUtensorMap tmB, CvParams p) {
+  extern __shared__ uint8_t cv_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(cv_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kSmemA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemA + 2 * kSmemB);
+  uint64_t* bar_a = bars + 0;
+  uint64_t* full_b = bars + 1;       // [2]
+  uint64_t* empty_b = bars + 3;      // [2]
+  uint64_t* tmem_full = bars + 5;    // [2]
+  uint64_t* tmem_empty = bars + 7;   // [2]
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.y;
+  const int m0 = blockIdx.x * kCvM;
+  const int fi = (int)p.ii[e], fj = (int)p.jj[e];
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(bar_a, kSmemA);
+      tma_load_3d(sA, &tmA, bar_a, m0, 0, fi);
+      tma_load_3d(sA + kBoxBytes, &tmA, bar_a, m0 + 64, 0, fi);
+      for (int c = 0; c < p.n_chunks; c++) {
+        const int s = c & 1;
+        if (c >= 2) mbar_wait(empty_b + s, ((c >> 1) - 1) & 1);
+        mbar_expect_tx(full_b + s, kSmemB);
+        for (int b = 0; b < 4; b++) tma_load_3d(sB + s * kSmemB + b * kBoxBytes, &tmB, full_b + s, c * kCvN + 64 * b, 0, fj);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = umma_idesc_f16(kCvM, kCvN);
+    mbar_wait(bar_a, 0);
+    for (int c = 0; c < p.n_chunks; c++) {
+      const int s = c & 1;
+      mbar_wait(full_b + s, (c >> 1) & 1);
+      if (c >= 2) mbar_wait(tmem_empty + s, ((c >> 1) - 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB + s * kSmemB);
+#pragma unroll
+        for (int k = 0; k < kCvK / 16; k++) {
+          const uint64_t ad = umma_desc_mn_sw128(a0 + k * 2048, kBoxBytes, 1024);
+          const uint64_t bd = umma_desc_mn_sw128(b0 + k * 2048, kBoxBytes, 1024);
+          umma_f16(tmem_base + s * kCvN, ad, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(empty_b + s);     // smem stage may be refilled when these MMAs have read it
+        umma_commit(tmem_full + s);   // accumulator ready for the epilogue
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;                                  // this thread's source pixel
+    const size_t row0 = ((size_t)e * p.HW + m) * (size_t)p.HW;         // level-0 row of m
+    const size_t row1 = ((size_t)e * p.HW + m) * (size_t)(p.HW / 4);
+    const size_t row2 = ((size_t)e * p.HW + m) * (size_t)(p.HW / 16);
+    const size_t row3 = ((size_t)e * p.HW + m) * (size_t)(p.HW / 64);
+    const int wd = p.wd;                                               // 64
+    uint32_t l1[2][16];                                                // the two level-1 rows of the current chunk, packed half2
+    uint32_t l2prev[8];                                                // level-2 row of the previous (even) chunk, packed half2
+    for (int c = 0; c < p.n_chunks; c++) {
+      const int s = c & 1;
+      mbar_wait(tmem_full + s, (c >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + s * kCvN + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int rp = 0; rp < 2; rp++) {                                 // two image rows (2 x 64 columns) at a time
+        uint32_t h[64];                                                // 128 level-0 values, packed half2: word w = columns (2w, 2w+1)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          uint32_t r[32];
+          tmem_ld32(tbase + rp * 128 + g * 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int k = 0; k < 16; k++) h[g * 16 + k] = pack_h2(__uint_as_float(r[2 * k]) * 0.0625f, __uint_as_float(r[2 * k + 1]) * 0.0625f);
+        }
+        // level 0: 128 halves = 256 contiguous bytes of this pixel's row
+        uint4* dst0 = reinterpret_cast<uint4*>(p.out0 + row0 + (size_t)c * kCvN + rp * 128);
+#pragma unroll
+        for (int v = 0; v < 16; v++) dst0[v] = make_uint4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]);
+        // level 1: image rows (4c + 2rp, 4c + 2rp + 1) -> level-1 row 2c + rp; word x of row r0 holds columns (2x, 2x+1)
+#pragma unroll
+        for (int x = 0; x < 16; x++) l1[rp][x] = pack_hh(avg4w(h[2 * x], h[32 + 2 * x]), avg4w(h[2 * x + 1], h[32 + 2 * x + 1]));
+        uint4* dst1 = reinterpret_cast<uint4*>(p.out1 + row1 + (size_t)(2 * c + rp) * (wd / 2));
+#pragma unroll
+        for (int v = 0; v < 4; v++) dst1[v] = make_uint4(l1[rp][4 * v], l1[rp][4 * v + 1], l1[rp][4 * v + 2], l1[rp][4 * v + 3]);
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + s);
+      // level 2: level-1 rows (2c, 2c+1) -> level-2 row c
+      uint32_t l2[8];
+#pragma unroll
+      for (int x = 0; x < 8; x++) l2[x] = pack_hh(avg4w(l1[0][2 * x], l1[1][2 * x]), avg4w(l1[0][2 * x + 1], l1[1][2 * x + 1]));
+      uint4* dst2 = reinterpret_cast<uint4*>(p.out2 + row2 + (size_t)c * (wd / 4));
+      dst2[0] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+      dst2[1] = make_uint4(l2[4], l2[5], l2[6], l2[7]);
+      if (c & 1) {   // level 3: level-2 rows (c-1, c) -> level-3 row c/2
+        uint32_t l3[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) l3[x] = pack_hh(avg4w(l2prev[2 * x], l2[2 * x]), avg4w(l2prev[2 * x + 1], l2[2 * x + 1]));
+        *reinterpret_cast<uint4*>(p.out3 + row3 + (size_t)(c >> 1) * (wd / 8)) = make_uint4(l3[0], l3[1], l3[2], l3[3]);
+      } else {
+#pragma unroll
+        for (int x = 0; x < 8; x++) l2prev[x] = l2[x];
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static int make_fmap_tensor_map(CUtensorMap* map, const void* base, int n_frames, int C, int HW) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return DBA_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)n_frames};
+  cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)HW * C * 2};       // bytes, dims 1..2
+  cuuint32_t box[3] = {64, (cuuint32_t)C, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DBA_ERR_CUDA; }
+  return DBA_OK;
+}
+
+}  // namespace dba
+using namespace dba;
+
+extern "C" int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj, void* out0, void* out1,
+                                       void* out2, void* out3, int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd,
+                                       int dtype, dba_stream_t stream) {
+  DBA_CHECK_ARG(n_edges >= 0 && n_frames1 > 0 && n_frames2 > 0, "bad extents");
+  DBA_CHECK_ARG(dtype == DBA_F16, "corr_volume_pyramid: only f16 features (the live system's autocast dtype) are implemented");
+  DBA_CHECK_ARG(channels == 128, "corr_volume_pyramid: 128 feature channels expected (reference fnet)");
+  DBA_CHECK_ARG(wd == 64 && ht % 8 == 0 && ht > 0, "corr_volume_pyramid: implemented for wd = 64, ht % 8 == 0 (512-wide inputs at 1/8 resolution)");
+  if (n_edges == 0) return DBA_OK;
+  DBA_CHECK_ARG(fmap1 && fmap2 && ii && jj && out0 && out1 && out2 && out3, "null pointer");
+  DBA_CHECK_ARG((((uintptr_t)fmap1 | (uintptr_t)fmap2 | (uintptr_t)out0 | (uintptr_t)out1 | (uintptr_t)out2 | (uintptr_t)out3) & 15) == 0, "pointers must be 16-byte aligned");
+  DBA_CHECK_ARG(n_edges <= 65535, "more than 65535 edges per call");
+  const int HW = ht * wd;
+  CUtensorMap tmA, tmB;
+  int rc = make_fmap_tensor_map(&tmA, fmap1, n_frames1, channels, HW); if (rc) return rc;
+  rc = make_fmap_tensor_map(&tmB, fmap2, n_frames2, channels, HW); if (rc) return rc;
+  static bool attr = false;
+  if (!attr) { DBA_CHECK_CUDA(cudaFuncSetAttribute(corr_volume_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem), "corr_volume smem attr"); attr = true; }
+  CvParams p;
+  p.ii = ii; p.jj = jj; p.out0 = (__half*)out0; p.out1 = (__half*)out1; p.out2 = (__half*)out2; p.out3 = (__half*)out3;
+  p.HW = HW; p.wd = wd; p.n_chunks = HW / kCvN;
+  dim3 grid(HW / kCvM, n_edges);
+  corr_volume_pyramid_kernel<<<grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  DBA_CHECK_LAUNCH("corr_volume_pyramid");
+  return DBA_OK;
+}

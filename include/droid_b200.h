@@ -50,6 +50,16 @@ int dba_corr_index_forward(const void* volume, const float* coords, void* corr,
 int dba_corr_index_backward(const float* coords, const void* corr_grad, void* volume_grad,
                             int n, int h1, int w1, int h2, int w2, int radius, int dtype, dba_stream_t stream);
 
+/* ---- correlation volume + pooled pyramid (tensor cores) -----------------------------------------------
+ * replaces CorrBlock.__init__ / CorrBlock.corr (reference droid_slam/modules/corr.py:24-38,63-71: torch.matmul of the
+ * /4-scaled feature maps + 3x avg_pool2d).  fmap1 [n_frames1,C,ht,wd], fmap2 [n_frames2,C,ht,wd] (f16, C = 128),
+ * ii,jj [E] int64 frame indices into fmap1 / fmap2;  out_l [E,ht,wd,ht/2^l,wd/2^l] f16 for l = 0..3, fully overwritten.
+ * One tcgen05/TMEM/TMA kernel writes all four levels in a single pass over the accumulator.
+ * Implemented for wd = 64, ht % 8 == 0 (DBA_ERR_INVALID otherwise). */
+int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj,
+                            void* out0, void* out1, void* out2, void* out3,
+                            int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd, int dtype, dba_stream_t stream);
+
 /* ---- on-the-fly correlation ---------------------------------------------------------------------
  * replaces altcorr_cuda_forward / altcorr_cuda_backward (reference src/altcorr_kernel.cu:132-225, bound at
  * src/droid.cpp:198-226).

@@ -267,3 +267,26 @@ def test_cluster_cholesky_solver_matches_fp64_lapack(capi, n):
     Hbad_ = Hbad.to(dev)
     c_api.check(capi.dba_solve_spd(ptr(Hbad_), ptr(bd_), n, 0.0, 0.0, ptr(x), ptr(fail), ptr(ws), ws.numel(), stream()), "solve_spd")
     assert int(fail) == 1 and float(x.abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_corr_volume_pyramid_tcgen05_matches_reference_formula(backends):
+    """CorrBlock.__init__ (reference modules/corr.py:24-38,63-71) in one tcgen05/TMEM/TMA kernel vs matmul + avg_pool2d"""
+    g = torch.Generator().manual_seed(31)
+    N, C, ht, wd = 5, 128, 16, 64
+    fmaps = torch.randn(N, C, ht, wd, generator=g).half()
+    ii = torch.tensor([0, 1, 2, 4, 3, 0]); jj = torch.tensor([1, 0, 4, 2, 3, 4])
+    got = backends.corr_volume_pyramid(fmaps.to(dev), fmaps.to(dev), ii.to(dev), jj.to(dev))
+    ref = oracle.corr_pyramid(fmaps[None, ii].float(), fmaps[None, jj].float(), num_levels=4)      # fp32 math on the fp16 inputs
+    assert len(got) == 4
+    for l in range(4):
+        assert got[l].shape == (6, ht, wd, ht >> l, wd >> l)
+        r = ref[l]
+        err = (got[l].float().cpu() - r).abs().max()
+        assert float(err) < 2e-2 + 2e-3 * float(r.abs().max()), (l, float(err))      # fp16 rounding of each level (values ~ +-30)
+    # against the same pipeline on the GPU in fp16 (what the live system computes with cuBLAS + avg_pool2d)
+    f = fmaps.to(dev)
+    corr = torch.matmul((f[ii].reshape(6, C, -1) / 4.0).transpose(1, 2), f[jj].reshape(6, C, -1) / 4.0).reshape(6 * ht * wd, 1, ht, wd)
+    for l in range(4):
+        assert float((got[l].reshape(-1).float() - corr.reshape(-1).float()).abs().max()) < 6e-2
+        corr = torch.nn.functional.avg_pool2d(corr, 2, stride=2)
