@@ -3,7 +3,8 @@
 // Replaces CorrBlock.__init__ / CorrBlock.corr (reference droid_slam/modules/corr.py:24-38, 63-71): a cuBLAS batched GEMM
 // writing the [E,HW,HW] level-0 volume followed by three avg_pool2d passes that re-read it.  Here, per edge e:
 //     L0[m][n]  = fp16( (1/16) * sum_c f1[ii[e]][c][m] * f2[jj[e]][c][n] )           (fp32 accumulation in TMEM)
-//     L1..L3    = 2x2 average pooling over n = (y2,x2), each level from the fp16-rounded level below (like ATen)
+//     L1..L3    = 2x2 average pooling over n = (y2,x2) (ATen rounds every level to fp16 before pooling the next; here the
+//                 cascade runs in fp32 on the accumulator and each level is rounded once -- closer to exact, within fp16 ulp)
 // are produced by one kernel: the GEMM is write bound (2*HW^2*128 flop vs 1.33*HW^2*2 bytes per edge, ~150 flop/B, far
 // below the B200 ridge), so the pyramid is computed in the epilogue from the accumulator while it is still on chip and the
 // volume is written exactly once (25.1 MB/edge at 48x64 instead of ~50 MB of traffic for GEMM + 3 pooling passes).
@@ -12,14 +13,14 @@
 // [128 ch x 128 px] once, then B chunks [128 ch x 256 px] (= 4 image rows of frame j), double buffered.  Warp 1: MMA issuer,
 // tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16 x 8, both operands MN-major straight from the [C,H,W] feature
 // layout (no transposes anywhere), two 256-column fp32 accumulators in TMEM so the MMA of chunk c+1 overlaps the epilogue of
-// chunk c.  Warps 2-5: epilogue, tcgen05.ld 32 lanes x 32 columns, thread = one source pixel row m, which makes every
-// pooling window thread-local (registers only).
+// chunk c.  Warps 2-9: epilogue, tcgen05.ld 32 lanes x 32 columns, thread = one source pixel row m x half an image row, which
+// makes every pooling window thread-local (registers only); outputs leave as 256-bit stores.
 #include "common.cuh"
 #include <cuda.h>
 
 namespace dba {
 
-constexpr int kCvThreads = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kCvThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
 constexpr int kCvM = 128;                // source pixels per CTA
 constexpr int kCvN = 256;                // target pixels per chunk (4 image rows at wd = 64)
 constexpr int kCvK = 128;                // channels
@@ -111,13 +112,10 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&t);
 }
-__device__ __forceinline__ uint32_t pack_hh(__half lo, __half hi) { return (uint32_t)__half_as_ushort(lo) | ((uint32_t)__half_as_ushort(hi) << 16); }
-// 2x2 average: `top` and `bot` are half2 words holding two horizontally adjacent values of two vertically adjacent rows;
-// fp32 accumulate, rounded to fp16 (ATen avg_pool2d on half tensors)
-__device__ __forceinline__ __half avg4w(uint32_t top, uint32_t bot) {
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&top));
-  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&bot));
-  return __float2half_rn((a.x + a.y + b.x + b.y) * 0.25f);
+// 256-bit global store (sm_100: st.global.v8.b32): one full 32-byte sector per thread per instruction
+__device__ __forceinline__ void st_v8(__half* dst, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]),
+               "r"(w[6]), "r"(w[7]) : "memory");
 }
 
 __global__ void __launch_bounds__(kCvThreads, 1) corr_volume_pyramid_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -141,7 +139,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) corr_volume_pyramid_kernel(cons
 
   if (threadIdx.x == 0) {
     mbar_init(bar_a, 1);
-    for (int s = 0; s < 2; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    for (int s = 0; s < 2; s++) { mbar_init(full_b + s, 1); mbar_init(empty_b + s, 1); mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: 512 columns = two 128x256 fp32 accumulators
@@ -189,62 +187,65 @@ __global__ void __launch_bounds__(kCvThreads, 1) corr_volume_pyramid_kernel(cons
       __syncwarp();
     }
   } else {
-    // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    // ================= epilogue: warps 2..9.  TMEM lane quarter q = warp % 4 (hardware rule); the two warps of a quarter
+    // split every image row of frame j into its left / right 32 columns, so all 2x2 / 4x4 / 8x8 pooling windows stay
+    // thread-local.  Pooling runs in fp32 on the accumulator values and is rounded once per level. =================
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;                                  // 0: columns 0..31, 1: columns 32..63 of each image row
     const int m = m0 + q * 32 + lane;                                  // this thread's source pixel
-    const size_t row0 = ((size_t)e * p.HW + m) * (size_t)p.HW;         // level-0 row of m
-    const size_t row1 = ((size_t)e * p.HW + m) * (size_t)(p.HW / 4);
-    const size_t row2 = ((size_t)e * p.HW + m) * (size_t)(p.HW / 16);
-    const size_t row3 = ((size_t)e * p.HW + m) * (size_t)(p.HW / 64);
     const int wd = p.wd;                                               // 64
-    uint32_t l1[2][16];                                                // the two level-1 rows of the current chunk, packed half2
-    uint32_t l2prev[8];                                                // level-2 row of the previous (even) chunk, packed half2
+    __half* o0 = p.out0 + ((size_t)e * p.HW + m) * (size_t)p.HW + half * 32;
+    __half* o1 = p.out1 + ((size_t)e * p.HW + m) * (size_t)(p.HW / 4) + half * 16;
+    __half* o2 = p.out2 + ((size_t)e * p.HW + m) * (size_t)(p.HW / 16) + half * 8;
+    __half* o3 = p.out3 + ((size_t)e * p.HW + m) * (size_t)(p.HW / 64) + half * 4;
+    const float sc = 0.0625f;                                          // (f1/4).(f2/4)
+    float l2prev[8];
     for (int c = 0; c < p.n_chunks; c++) {
       const int s = c & 1;
       mbar_wait(tmem_full + s, (c >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tbase = tmem_base + s * kCvN + ((uint32_t)(q * 32) << 16);
+      const uint32_t tbase = tmem_base + s * kCvN + ((uint32_t)(q * 32) << 16) + half * 32;
+      float l1f[2][16];
 #pragma unroll
-      for (int rp = 0; rp < 2; rp++) {                                 // two image rows (2 x 64 columns) at a time
-        uint32_t h[64];                                                // 128 level-0 values, packed half2: word w = columns (2w, 2w+1)
+      for (int rp = 0; rp < 2; rp++) {                                 // image rows 4c + 2rp, 4c + 2rp + 1
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tbase + (2 * rp) * 64, ra);
+        tmem_ld32(tbase + (2 * rp + 1) * 64, rb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t wa[16], wb[16];
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-          uint32_t r[32];
-          tmem_ld32(tbase + rp * 128 + g * 32, r);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int k = 0; k < 16; k++) h[g * 16 + k] = pack_h2(__uint_as_float(r[2 * k]) * 0.0625f, __uint_as_float(r[2 * k + 1]) * 0.0625f);
+        for (int k = 0; k < 16; k++) {
+          wa[k] = pack_h2(__uint_as_float(ra[2 * k]) * sc, __uint_as_float(ra[2 * k + 1]) * sc);
+          wb[k] = pack_h2(__uint_as_float(rb[2 * k]) * sc, __uint_as_float(rb[2 * k + 1]) * sc);
+          l1f[rp][k] = ((__uint_as_float(ra[2 * k]) + __uint_as_float(ra[2 * k + 1])) + (__uint_as_float(rb[2 * k]) + __uint_as_float(rb[2 * k + 1]))) * (0.25f * sc);
         }
-        // level 0: 128 halves = 256 contiguous bytes of this pixel's row
-        uint4* dst0 = reinterpret_cast<uint4*>(p.out0 + row0 + (size_t)c * kCvN + rp * 128);
+        // level 0: 32 halves = 64 contiguous bytes per image row, as 256-bit stores (one full 32-byte sector each)
+        st_v8(o0 + (size_t)c * kCvN + (2 * rp) * 64, wa);      st_v8(o0 + (size_t)c * kCvN + (2 * rp) * 64 + 16, wa + 8);
+        st_v8(o0 + (size_t)c * kCvN + (2 * rp + 1) * 64, wb);  st_v8(o0 + (size_t)c * kCvN + (2 * rp + 1) * 64 + 16, wb + 8);
+        // level 1 row 2c + rp: 16 halves = 32 bytes
+        uint32_t w1[8];
 #pragma unroll
-        for (int v = 0; v < 16; v++) dst0[v] = make_uint4(h[4 * v], h[4 * v + 1], h[4 * v + 2], h[4 * v + 3]);
-        // level 1: image rows (4c + 2rp, 4c + 2rp + 1) -> level-1 row 2c + rp; word x of row r0 holds columns (2x, 2x+1)
-#pragma unroll
-        for (int x = 0; x < 16; x++) l1[rp][x] = pack_hh(avg4w(h[2 * x], h[32 + 2 * x]), avg4w(h[2 * x + 1], h[32 + 2 * x + 1]));
-        uint4* dst1 = reinterpret_cast<uint4*>(p.out1 + row1 + (size_t)(2 * c + rp) * (wd / 2));
-#pragma unroll
-        for (int v = 0; v < 4; v++) dst1[v] = make_uint4(l1[rp][4 * v], l1[rp][4 * v + 1], l1[rp][4 * v + 2], l1[rp][4 * v + 3]);
+        for (int k = 0; k < 8; k++) w1[k] = pack_h2(l1f[rp][2 * k], l1f[rp][2 * k + 1]);
+        st_v8(o1 + (size_t)(2 * c + rp) * (wd / 2), w1);
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + s);
-      // level 2: level-1 rows (2c, 2c+1) -> level-2 row c
-      uint32_t l2[8];
+      // level 2 row c: 8 halves = 16 bytes
+      float l2f[8];
 #pragma unroll
-      for (int x = 0; x < 8; x++) l2[x] = pack_hh(avg4w(l1[0][2 * x], l1[1][2 * x]), avg4w(l1[0][2 * x + 1], l1[1][2 * x + 1]));
-      uint4* dst2 = reinterpret_cast<uint4*>(p.out2 + row2 + (size_t)c * (wd / 4));
-      dst2[0] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
-      dst2[1] = make_uint4(l2[4], l2[5], l2[6], l2[7]);
-      if (c & 1) {   // level 3: level-2 rows (c-1, c) -> level-3 row c/2
-        uint32_t l3[4];
+      for (int k = 0; k < 8; k++) l2f[k] = ((l1f[0][2 * k] + l1f[0][2 * k + 1]) + (l1f[1][2 * k] + l1f[1][2 * k + 1])) * 0.25f;
+      *reinterpret_cast<uint4*>(o2 + (size_t)c * (wd / 4)) =
+          make_uint4(pack_h2(l2f[0], l2f[1]), pack_h2(l2f[2], l2f[3]), pack_h2(l2f[4], l2f[5]), pack_h2(l2f[6], l2f[7]));
+      if (c & 1) {   // level 3 row c/2: 4 halves = 8 bytes
+        float l3f[4];
 #pragma unroll
-        for (int x = 0; x < 4; x++) l3[x] = pack_hh(avg4w(l2prev[2 * x], l2[2 * x]), avg4w(l2prev[2 * x + 1], l2[2 * x + 1]));
-        *reinterpret_cast<uint4*>(p.out3 + row3 + (size_t)(c >> 1) * (wd / 8)) = make_uint4(l3[0], l3[1], l3[2], l3[3]);
+        for (int k = 0; k < 4; k++) l3f[k] = ((l2prev[2 * k] + l2prev[2 * k + 1]) + (l2f[2 * k] + l2f[2 * k + 1])) * 0.25f;
+        *reinterpret_cast<uint2*>(o3 + (size_t)(c >> 1) * (wd / 8)) = make_uint2(pack_h2(l3f[0], l3f[1]), pack_h2(l3f[2], l3f[3]));
       } else {
 #pragma unroll
-        for (int x = 0; x < 8; x++) l2prev[x] = l2[x];
+        for (int k = 0; k < 8; k++) l2prev[k] = l2f[k];
       }
     }
   }
