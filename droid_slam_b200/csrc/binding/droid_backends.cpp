@@ -232,6 +232,20 @@ std::vector<torch::Tensor> corr_volume_pyramid(torch::Tensor fmap1, torch::Tenso
   return out;
 }
 
+// extension: fused DepthVideo.reproject (reference depth_video.py:171-179 -> geom/projective_ops.py:165-198, jacobian=False)
+std::vector<torch::Tensor> reproject(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor ii, torch::Tensor jj) {
+  CHECK_INPUT(poses); CHECK_INPUT(disps); CHECK_INPUT(intrinsics); CHECK_INPUT(ii); CHECK_INPUT(jj);
+  CHECK_F32(poses); CHECK_F32(disps); CHECK_F32(intrinsics); CHECK_I64(ii); CHECK_I64(jj);
+  TORCH_CHECK(disps.dim() == 3 && intrinsics.dim() == 2 && intrinsics.size(1) == 4, "disps [N,ht,wd], intrinsics [N,4]");
+  c10::cuda::CUDAGuard guard(poses.device());
+  const int num = (int)ii.size(0), ht = (int)disps.size(1), wd = (int)disps.size(2);
+  auto coords = torch::empty({num, ht, wd, 2}, poses.options());
+  auto valid = torch::empty({num, ht, wd, 1}, poses.options());
+  check_status(dba_reproject(poses.data_ptr<float>(), disps.data_ptr<float>(), intrinsics.data_ptr<float>(), ii.data_ptr<int64_t>(),
+                             jj.data_ptr<int64_t>(), coords.data_ptr<float>(), valid.data_ptr<float>(), num, ht, wd, cur_stream()), "reproject");
+  return {coords, valid};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native droid_backends (drop-in for princeton-vl/DROID-SLAM src/droid.cpp)";
   // bundle adjustment kernels
@@ -246,5 +260,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("corr_index_forward", &corr_index_forward, "INDEX forward");
   m.def("corr_index_backward", &corr_index_backward, "INDEX backward");
   m.def("corr_volume_pyramid", &corr_volume_pyramid, "all-pairs correlation + 4-level pyramid (tcgen05), B200 extension");
+  m.def("reproject", &reproject, "fused pops.projective_transform(jacobian=False), B200 extension");
   m.def("_b200_native", []() { return true; });
 }

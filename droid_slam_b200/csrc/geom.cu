@@ -151,8 +151,51 @@ __global__ void __launch_bounds__(256) iproj_kernel(const float* __restrict__ po
   p[0] = Xj[0] / Xj[3]; p[1] = Xj[1] / Xj[3]; p[2] = Xj[2] / Xj[3];
 }
 
+// Fused reprojection of the update operator's input (replaces the ~10 torch/lietorch launches of
+// pops.projective_transform(..., jacobian=False), reference droid_slam/geom/projective_ops.py:165-198, called through
+// DepthVideo.reproject, depth_video.py:171-179):  coords = proj(G_j G_i^-1 iproj(d_i)), valid = Z > 0.2.
+// Differences from projmap that this path has in the reference and that are kept: per-frame intrinsics (iproj with frame
+// ii's, proj with frame jj's), stereo edges ii == jj use the fixed baseline (-0.1,0,0 | identity) (:176-178), MIN_DEPTH is 0.2
+// and depths below 0.1 are replaced by 1 before the division (:52,185)  (quirk Q3).
+__global__ void __launch_bounds__(256) reproject_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
+                                                        const float* __restrict__ intr, const int64_t* __restrict__ ii,
+                                                        const int64_t* __restrict__ jj, float* __restrict__ coords,
+                                                        float* __restrict__ valid, int ht, int wd) {
+  const int e = blockIdx.y;
+  __shared__ float T[7];
+  const int ix = (int)ii[e], jx = (int)jj[e];
+  if (threadIdx.x == 0) edge_transform(poses, ix, jx, /*stereo_quirk=*/true, T, T + 3);
+  __syncthreads();
+  const Intr Ki = load_intr(intr + 4 * (size_t)ix), Kj = load_intr(intr + 4 * (size_t)jx);
+  const int hw = ht * wd;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= hw) return;
+  const int i = k / wd, j = k - i * wd;
+  float Xi[4] = {((float)j - Ki.cx) / Ki.fx, ((float)i - Ki.cy) / Ki.fy, 1.f, __ldg(disps + (size_t)ix * hw + k)}, Xj[4];
+  act_se3(T, T + 3, Xi, Xj);
+  const float Z = (Xj[2] < 0.5f * 0.2f) ? 1.f : Xj[2];
+  const float d = 1.0f / Z;
+  float2 c;
+  c.x = Kj.fx * (Xj[0] * d) + Kj.cx;
+  c.y = Kj.fy * (Xj[1] * d) + Kj.cy;
+  reinterpret_cast<float2*>(coords)[(size_t)e * hw + k] = c;
+  valid[(size_t)e * hw + k] = (Xj[2] > 0.2f) ? 1.f : 0.f;
+}
+
 }  // namespace dba
 using namespace dba;
+
+extern "C" int dba_reproject(const float* poses, const float* disps, const float* intrinsics_per_frame, const int64_t* ii, const int64_t* jj,
+                             float* coords, float* valid, int n_edges, int ht, int wd, dba_stream_t stream) {
+  DBA_CHECK_ARG(n_edges >= 0 && ht >= 0 && wd >= 0, "negative extent");
+  if (n_edges == 0 || ht * wd == 0) return DBA_OK;
+  DBA_CHECK_ARG(poses && disps && intrinsics_per_frame && ii && jj && coords && valid, "null pointer");
+  DBA_CHECK_ARG(n_edges <= 65535, "more than 65535 edges in one reproject call");
+  dim3 grid((ht * wd + 255) / 256, n_edges);
+  reproject_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics_per_frame, ii, jj, coords, valid, ht, wd);
+  DBA_CHECK_LAUNCH("reproject");
+  return DBA_OK;
+}
 
 extern "C" int dba_projmap(const float* poses, const float* disps, const float* intrinsics, const int64_t* ii, const int64_t* jj,
                            float* coords, float* valid, int n_edges, int ht, int wd, dba_stream_t stream) {

@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from . import install
 
-__all__ = ["CorrBlock", "AltCorrBlock"]
+__all__ = ["CorrBlock", "AltCorrBlock", "reproject"]
 
 
 class CorrBlock:
@@ -86,3 +86,13 @@ class AltCorrBlock:
             corr, = self._be.altcorr_forward(self.pyramid[0].contiguous(), self.pyramid[i].contiguous(), (coords / 2 ** i).contiguous(), ii, jj, self.radius)
             corr_list.append(corr.flatten(2, 3))
         return torch.stack(corr_list, dim=2).flatten(2, 3)
+
+
+def reproject(poses, disps, intrinsics, ii, jj):
+    """DepthVideo.reproject (reference droid_slam/depth_video.py:171-179) in one kernel: poses [N,7], disps [N,ht,wd],
+    intrinsics [N,4], ii/jj index tensors or lists -> (coords [1,E,ht,wd,2], valid [1,E,ht,wd,1]) like the reference."""
+    be = install()
+    ii = torch.as_tensor(ii).to(device=poses.device, dtype=torch.long).reshape(-1)
+    jj = torch.as_tensor(jj).to(device=poses.device, dtype=torch.long).reshape(-1)
+    coords, valid = be.reproject(poses.contiguous(), disps.contiguous(), intrinsics.contiguous(), ii, jj)
+    return coords[None], valid[None]

@@ -84,6 +84,11 @@ int dba_altcorr_backward(const void* fmap1, const void* fmap2, const float* coor
 int dba_projmap(const float* poses, const float* disps, const float* intrinsics,
                 const int64_t* ii, const int64_t* jj, float* coords /*[E,ht,wd,3]*/, float* valid /*[E,ht,wd,1]*/,
                 int n_edges, int ht, int wd, dba_stream_t stream);
+/* fused reprojection feeding the update operator: replaces pops.projective_transform(jacobian=False)
+ * (reference droid_slam/geom/projective_ops.py:165-198 via DepthVideo.reproject, depth_video.py:171-179).
+ * intrinsics_per_frame [n_frames,4]; coords [E,ht,wd,2], valid [E,ht,wd,1]; MIN_DEPTH 0.2, stereo baseline for ii == jj. */
+int dba_reproject(const float* poses, const float* disps, const float* intrinsics_per_frame,
+                  const int64_t* ii, const int64_t* jj, float* coords, float* valid, int n_edges, int ht, int wd, dba_stream_t stream);
 int dba_frame_distance(const float* poses, const float* disps, const float* intrinsics,
                        const int64_t* ii, const int64_t* jj, float* dist /*[K]*/,
                        int n_pairs, int ht, int wd, float beta, dba_stream_t stream);

@@ -3,7 +3,7 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py)."""
 import torch
 from .se3 import act_se3, rel_se3
 
-__all__ = ["projmap", "frame_distance", "depth_filter", "iproj", "MIN_DEPTH", "pixel_grid", "edge_transform"]
+__all__ = ["projmap", "frame_distance", "depth_filter", "iproj", "MIN_DEPTH", "pixel_grid", "edge_transform", "reproject"]
 
 MIN_DEPTH = 0.25  # src/droid_kernels.cu:35
 
@@ -129,3 +129,26 @@ def iproj(poses, disps, intrinsics):
     Xj = act_se3(poses[:n, None, :3], poses[:n, None, 3:], Xi)
     pts = Xj[..., :3] / Xj[..., 3:4]
     return pts.reshape(n, ht, wd, 3)
+
+
+def reproject(poses, disps, intrinsics, ii, jj):
+    """pops.projective_transform(poses, depths, intrinsics, ii, jj, jacobian=False) as called by DepthVideo.reproject
+    (droid_slam/geom/projective_ops.py:165-198, depth_video.py:171-179), restated without lietorch:
+    X0 = iproj(d_i; K_i) (:16-35), Gij = G_j G_i^-1 with the stereo constant for ii == jj (:174-178), X1 = Gij X0,
+    proj with Z < 0.1 -> 1 and K_j (:46-58), valid = (X1.Z > 0.2) & (X0.Z > 0.2) (:185).  intrinsics [N,4]."""
+    N, ht, wd = disps.shape
+    E = ii.shape[0]
+    dt = disps.dtype
+    tij, qij = edge_transform(poses, ii, jj, stereo_quirk=True)
+    u, v = pixel_grid(ht, wd, dt)
+    Ki, Kj = intrinsics[ii], intrinsics[jj]
+    d_i = disps[ii].reshape(E, -1)
+    X0 = torch.stack([(u[None] - Ki[:, 2:3]) / Ki[:, 0:1], (v[None] - Ki[:, 3:4]) / Ki[:, 1:2], torch.ones_like(d_i), d_i], dim=-1)
+    X1 = act_se3(tij[:, None], qij[:, None], X0)
+    Z = torch.where(X1[..., 2] < 0.5 * 0.2, torch.ones_like(X1[..., 2]), X1[..., 2])
+    d = 1.0 / Z
+    x = Kj[:, 0:1] * (X1[..., 0] * d) + Kj[:, 2:3]
+    y = Kj[:, 1:2] * (X1[..., 1] * d) + Kj[:, 3:4]
+    coords = torch.stack([x, y], dim=-1).reshape(E, ht, wd, 2)
+    valid = ((X1[..., 2] > 0.2) & (X0[..., 2] > 0.2)).to(dt).reshape(E, ht, wd, 1)
+    return coords, valid

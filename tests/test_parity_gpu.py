@@ -315,3 +315,17 @@ def test_corrblock_mirror_matches_oracle_lookup():
     assert torch.equal(blk2(coords.to(dev)), got)
     sub = blk2[torch.tensor([True, False, True, False, True], device=dev)]
     assert sub.corr_pyramid[0].shape[0] == 3
+
+
+def test_fused_reproject_matches_projective_transform_restatement(backends):
+    """A5: DepthVideo.reproject / pops.projective_transform(jacobian=False) in one kernel, incl. per-frame intrinsics, stereo edges
+    and the MIN_DEPTH = 0.2 / Z < 0.1 -> 1 quirk (Q3)"""
+    from droid_slam_b200.modules import reproject
+    s = _scene(E=30, N=9, ht=16, wd=24, stereo=True, seed=6)
+    K = s["intrinsics"][None].repeat(9, 1) * (1 + 0.01 * torch.arange(9)[:, None])      # per-frame intrinsics
+    P = s["poses"].clone(); P[4, 2] += 1.2                                               # push some points behind / close to a camera
+    c, v = reproject(P.to(dev), s["disps"].to(dev), K.to(dev), s["ii"], s["jj"])
+    rc, rv = oracle.reproject(P, s["disps"], K, s["ii"], s["jj"])
+    assert c.shape == (1, 30, 16, 24, 2) and v.shape == (1, 30, 16, 24, 1)
+    assert rel_err(c[0], rc, floor=1.0) < 1e-4 and frac_equal(v[0], rv) > 0.999
+    assert 0.05 < float(rv.mean()) < 1.0 and bool((s["ii"] == s["jj"]).any())
