@@ -160,6 +160,21 @@ __global__ void __launch_bounds__(256) ba_fill_csr_kernel(const int64_t* __restr
 // ---------------------------------------------------------------------------------------------------------
 // build: per (depth frame, pixel chunk): geometry of all out-edges, depth-block sums, per-edge pose blocks
 // ---------------------------------------------------------------------------------------------------------
+// total of value i ends up in lane i  (v[0] on return), 31 shuffles
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; i++) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 struct EdgeSm {
   float t[3], q[4];      // G_ij
   float A[36];           // Ji = -A Jj   (A = transposed adjoint, applied with the reference's adjSE3 arithmetic)
@@ -179,7 +194,7 @@ __device__ __forceinline__ void adj_se3(const float* t, const float* q, const fl
   Y[3] += v[0]; Y[4] += v[1]; Y[5] += v[2];
 }
 
-__global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
+__global__ void __launch_bounds__(kBuildThreads, 2) ba_build_kernel(
     const float* __restrict__ poses, const float* __restrict__ disps, const float* __restrict__ intr,
     const float* __restrict__ disps_sens, const float* __restrict__ targets, const float* __restrict__ weights,
     const float* __restrict__ eta, int eta_rows, int eta_by_frame, const int64_t* __restrict__ jj,
@@ -240,10 +255,40 @@ __global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
     }
     __syncthreads();
 
+    // software pipeline: the four target/weight loads of edge b+1 are in flight while edge b is computed
+    float nw_u[kPPT], nw_v[kPPT], nt_u[kPPT], nt_v[kPPT];
+    {
+      const int e0 = s_edge[0].e;
+#pragma unroll
+      for (int s = 0; s < kPPT; s++) {
+        const int p = pix[s];
+        const bool okp = p < HW;
+        nw_u[s] = okp ? __ldg(weights + ((size_t)e0 * 2 + 0) * HW + p) : 0.f;
+        nw_v[s] = okp ? __ldg(weights + ((size_t)e0 * 2 + 1) * HW + p) : 0.f;
+        nt_u[s] = okp ? __ldg(targets + ((size_t)e0 * 2 + 0) * HW + p) : 0.f;
+        nt_v[s] = okp ? __ldg(targets + ((size_t)e0 * 2 + 1) * HW + p) : 0.f;
+      }
+    }
     for (int b = 0; b < nb; b++) {
       const EdgeSm& S = s_edge[b];
       const float t0_ = S.t[0], t1_ = S.t[1], t2_ = S.t[2];
       const int e = S.e;
+      float cw_u[kPPT], cw_v[kPPT], ct_u[kPPT], ct_v[kPPT];
+#pragma unroll
+      for (int s = 0; s < kPPT; s++) { cw_u[s] = nw_u[s]; cw_v[s] = nw_v[s]; ct_u[s] = nt_u[s]; ct_v[s] = nt_v[s]; }
+      if (b + 1 < nb) {
+        const int e1 = s_edge[b + 1].e;
+#pragma unroll
+        for (int s = 0; s < kPPT; s++) {
+          const int p = pix[s];
+          if (p < HW) {
+            nw_u[s] = __ldg(weights + ((size_t)e1 * 2 + 0) * HW + p);
+            nw_v[s] = __ldg(weights + ((size_t)e1 * 2 + 1) * HW + p);
+            nt_u[s] = __ldg(targets + ((size_t)e1 * 2 + 0) * HW + p);
+            nt_v[s] = __ldg(targets + ((size_t)e1 * 2 + 1) * HW + p);
+          }
+        }
+      }
       const bool stereo = S.stereo != 0;
       float Hjj[21], vj[6];
 #pragma unroll
@@ -262,10 +307,10 @@ __global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
           const float d = close ? 0.f : 1.0f / Xj[2];
           const float d2 = d * d;
           // `.001 * weight`: fp64 product rounded to fp32 (reference :314-315)
-          float wu = close ? 0.f : (float)(.001 * (double)__ldg(weights + ((size_t)e * 2 + 0) * HW + p));
-          float wv = close ? 0.f : (float)(.001 * (double)__ldg(weights + ((size_t)e * 2 + 1) * HW + p));
-          const float ru = __ldg(targets + ((size_t)e * 2 + 0) * HW + p) - (fx * d * x + cx);
-          const float rv = __ldg(targets + ((size_t)e * 2 + 1) * HW + p) - (fy * d * y + cy);
+          float wu = close ? 0.f : (float)(.001 * (double)cw_u[s]);
+          float wv = close ? 0.f : (float)(.001 * (double)cw_v[s]);
+          const float ru = ct_u[s] - (fx * d * x + cx);
+          const float rv = ct_v[s] - (fy * d * y + cy);
           float Ju[6], Jv[6];
           Ju[0] = fx * (h * d); Ju[1] = fx * 0; Ju[2] = fx * (-x * h * d2);
           Ju[3] = fx * (-x * y * d2); Ju[4] = fx * (1 + x * x * d2); Ju[5] = fx * (-y * d);
@@ -303,11 +348,18 @@ __global__ void __launch_bounds__(kBuildThreads) ba_build_kernel(
           }
         }
       }
-      // warp reduction, one partial per warp
+      // warp reduction of the 27 sums (padded to 32): transpose-reduction, 31 shuffles; lane k ends with the total of value k
+      {
+        float v32[32];
 #pragma unroll
-      for (int k = 0; k < 21; k++) { const float v = warp_sum(Hjj[k]); if (lane == 0) s_part[warp][b][k] = v; }
+        for (int k = 0; k < 21; k++) v32[k] = Hjj[k];
 #pragma unroll
-      for (int k = 0; k < 6; k++) { const float v = warp_sum(vj[k]); if (lane == 0) s_part[warp][b][21 + k] = v; }
+        for (int k = 0; k < 6; k++) v32[21 + k] = vj[k];
+#pragma unroll
+        for (int k = 27; k < 32; k++) v32[k] = 0.f;
+        const float tot = transpose_reduce32(v32, lane);
+        if (lane < 27) s_part[warp][b][lane] = tot;
+      }
     }
     __syncthreads();
     // ---- cross-warp sums in fp64
@@ -391,21 +443,6 @@ constexpr int kSchurWarps = kSchurThreads / 32;
 constexpr int kSchurTP = 256;        // pixels per shared-memory tile
 constexpr int kSchurRB = 12;         // rows per block
 constexpr int kSchurMaxRows = 255;   // rows per frame (out-degree + 1); larger frames raise ST_BAD_INDEX
-
-// total of value i ends up in lane i  (v[0] on return), 31 shuffles
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; i++) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
 
 template <bool kSingle>
 __global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(

@@ -96,3 +96,25 @@ def test_stereo_config4_matches_oracle(backends):
     oracle.ba(P64, D64, s["intrinsics"], s["disps_sens"], s["targets"], s["weights"], s["eta"], s["ii"], s["jj"], s["t0"], s["t1"], 2,
               s["lm"], s["ep"], False, dtype=torch.float64)
     assert rel_err(P, P64, floor=1.0) < 1e-4 and rel_err(D, D64, floor=1.0) < 1e-4
+
+
+def test_stress_shape_72x96_bf16_and_ba(backends):
+    """BASELINE config 5 shapes (72x96 feature maps, bf16 volumes) at a reduced edge count: exercises wd = 96 (pyramid level 3 has
+    12-wide rows -> generic lookup path), HW = 6912 (not a multiple of the BA pixel chunk) and the bf16 extension."""
+    s = synth.make_scene(dict(E=40, N=10, ht=72, wd=96, stereo=False, itrs=2, lm=1e-4, ep=0.1), seed=8)
+    pyr, coords, _ = synth.make_corr_inputs(s, dtype=torch.bfloat16, device=dev, channels=32, edge_chunk=8)
+    for lvl, vol in enumerate(pyr):
+        c = (coords / 2 ** lvl).contiguous()
+        out, = backends.corr_index_forward(vol, c, 3)
+        ref, = oracle.corr_index_forward(vol[:2].float().cpu(), c[:2].cpu(), 3)          # bf16: fp32 math on bf16-rounded inputs
+        assert rel_err(out[:2].float(), ref, floor=float(ref.abs().max())) < 1e-2
+        f16, = backends.corr_index_forward(vol.half(), c, 3)
+        r16, = oracle.corr_index_forward(vol[:2].half().cpu(), c[:2].cpu(), 3)
+        assert torch.equal(f16[:2].cpu(), r16)
+    P, D = s["poses"].to(dev), s["disps"].to(dev)
+    args = [s[k].to(dev) for k in ("intrinsics", "disps_sens", "targets", "weights", "eta", "ii", "jj")]
+    backends.ba(P, D, *args, s["t0"], s["t1"], 2, s["lm"], s["ep"], False)
+    P64, D64 = s["poses"].double(), s["disps"].double()
+    oracle.ba(P64, D64, s["intrinsics"], s["disps_sens"], s["targets"], s["weights"], s["eta"], s["ii"], s["jj"], s["t0"], s["t1"], 2,
+              s["lm"], s["ep"], False, dtype=torch.float64)
+    assert rel_err(P, P64, floor=1.0) < 1e-4 and rel_err(D, D64, floor=1.0) < 1e-4
