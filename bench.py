@@ -416,6 +416,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner at INFO/VERSION)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         if args.impl == "reference":

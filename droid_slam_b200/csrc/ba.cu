@@ -20,12 +20,11 @@
 //     src/droid_kernels.cu:1114), then retraction of poses (left-multiplicative Exp, no renormalisation) and disps.
 #include "common.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace dba {
 
-constexpr int kPPT = 4;            // pixels per thread in the build kernel
 constexpr int kBuildThreads = 256;
-constexpr int kChunkPx = kPPT * kBuildThreads;   // 1024 pixels per CTA
 constexpr int kEdgeBatch = 16;     // edges whose transforms / partial sums live in shared memory at once
 
 struct Layout {
@@ -194,6 +193,7 @@ __device__ __forceinline__ void adj_se3(const float* t, const float* q, const fl
   Y[3] += v[0]; Y[4] += v[1]; Y[5] += v[2];
 }
 
+template <int kPPT>   // pixels per thread: 4 when many frames fill the GPU, fewer when a rank owns only a few source frames
 __global__ void __launch_bounds__(kBuildThreads, 2) ba_build_kernel(
     const float* __restrict__ poses, const float* __restrict__ disps, const float* __restrict__ intr,
     const float* __restrict__ disps_sens, const float* __restrict__ targets, const float* __restrict__ weights,
@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2) ba_build_kernel(
   float Cacc[kPPT], wacc[kPPT], Eiacc[kPPT][6];
 #pragma unroll
   for (int s = 0; s < kPPT; s++) {
-    const int p = blockIdx.x * kChunkPx + s * kBuildThreads + tid;
+    const int p = blockIdx.x * (kPPT * kBuildThreads) + s * kBuildThreads + tid;
     pix[s] = p;
     const bool ok = p < HW;
     const int i = ok ? p / wd : 0, j = ok ? p - i * wd : 0;
@@ -493,8 +493,10 @@ __global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
   if (px_begin >= px_end) return;
   const bool vec4 = (HW % 4) == 0;
 
+  int pair_id = 0;
   for (int bi = 0; bi < nblk; bi++) {
-    for (int bj = bi; bj < nblk; bj++) {
+    for (int bj = bi; bj < nblk; bj++, pair_id++) {
+      if ((pair_id % (int)gridDim.z) != (int)blockIdx.z) continue;        // block pairs are spread over gridDim.z CTAs
       const int ra = min(kSchurRB, nrows - bi * kSchurRB);
       const int rb = min(kSchurRB, nrows - bj * kSchurRB);
       const int npairs = (bi == bj) ? ra * (ra + 1) / 2 : ra * rb;
@@ -768,18 +770,27 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
   if (L.P == 0) return DBA_OK;
   double* Hsys = WS(double, L.off_sys);
   double* bsys = Hsys + (size_t)L.n * L.n;
-  dim3 grid((HW + kChunkPx - 1) / kChunkPx, a->n_frames);   // y: depth frames (CTAs beyond M exit immediately)
-  ba_build_kernel<<<grid, kBuildThreads, 0, st>>>(a->poses, a->disps, a->intrinsics, a->disps_sens, a->targets, a->weights, a->eta,
-                                                  a->eta_rows, a->eta_by_frame, a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
-                                                  WS(int, L.off_edgeidx), HW, a->wd, a->t0, L.P, a->motion_only, Hsys, bsys,
-                                                  WS(float, L.off_Eij), WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei));
+  // frames that can own edges on this rank (edge-sharded runs own a sub-range): size the pixel chunks so the grid fills the GPU
+  const int eff_frames = std::max(1, std::min(a->n_frames, a->own_hi - a->own_lo));
+  const int ppt = (eff_frames * ((HW + 4 * kBuildThreads - 1) / (4 * kBuildThreads)) >= 148) ? 4
+                : (eff_frames * ((HW + 2 * kBuildThreads - 1) / (2 * kBuildThreads)) >= 148) ? 2 : 1;
+#define LAUNCH_BUILD(PPT)                                                                                                               \
+  ba_build_kernel<PPT><<<dim3((HW + PPT * kBuildThreads - 1) / (PPT * kBuildThreads), a->n_frames), kBuildThreads, 0, st>>>(             \
+      a->poses, a->disps, a->intrinsics, a->disps_sens, a->targets, a->weights, a->eta, a->eta_rows, a->eta_by_frame, a->jj, WS(int, L.off_hdr),  \
+      WS(int, L.off_kx), WS(int, L.off_rowptr), WS(int, L.off_edgeidx), HW, a->wd, a->t0, L.P, a->motion_only, Hsys, bsys,               \
+      WS(float, L.off_Eij), WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei))
+  if (ppt == 4) LAUNCH_BUILD(4); else if (ppt == 2) LAUNCH_BUILD(2); else LAUNCH_BUILD(1);
+#undef LAUNCH_BUILD
   DBA_CHECK_LAUNCH("ba_build");
   if (!a->motion_only) {
     const int tiles = (HW + kSchurTP - 1) / kSchurTP;
-    int chunks = (2 * 148 + a->n_frames - 1) / a->n_frames;          // about two CTAs per SM worth of (frame, chunk) work items
+    int chunks = (2 * 148 + eff_frames - 1) / eff_frames;          // about two CTAs per SM worth of (frame, chunk) work items
     chunks = chunks < 1 ? 1 : (chunks > tiles ? tiles : chunks);
     const int px_per_cta = ((tiles + chunks - 1) / chunks) * kSchurTP;
-    dim3 g2((HW + px_per_cta - 1) / px_per_cta, a->n_frames);
+    const int gx = (HW + px_per_cta - 1) / px_per_cta;
+    // frames with more than 12 rows are processed as pairs of 12-row blocks; when few frames carry many edges (edge-sharded
+    // ranks, dense graphs) the block pairs are spread over gridDim.z so the GPU stays full
+    const int zsplit = (eff_frames * gx >= 2 * 148) ? 1 : std::min(16, (4 * 148 + eff_frames * gx - 1) / (eff_frames * gx));
     const size_t smem1 = ((size_t)kSchurRB * 6 * kSchurTP + 2 * kSchurTP + (size_t)(kSchurRB * (kSchurRB + 1) / 2) * 42) * sizeof(float);
     const size_t smem2 = ((size_t)2 * kSchurRB * 6 * kSchurTP + 2 * kSchurTP + (size_t)(kSchurRB * kSchurRB) * 42) * sizeof(float);
     static bool attr_set = false;
@@ -788,11 +799,11 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
       DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur smem attr");
       attr_set = true;
     }
-    ba_schur_kernel<true><<<g2, kSchurThreads, smem1, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+    ba_schur_kernel<true><<<dim3(gx, a->n_frames, 1), kSchurThreads, smem1, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
                                                            WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
     DBA_CHECK_LAUNCH("ba_schur<single>");
-    ba_schur_kernel<false><<<g2, kSchurThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+    ba_schur_kernel<false><<<dim3(gx, a->n_frames, zsplit), kSchurThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                             WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
                                                             WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
     DBA_CHECK_LAUNCH("ba_schur<multi>");
