@@ -444,6 +444,37 @@ constexpr int kSchurTP = 256;        // pixels per shared-memory tile
 constexpr int kSchurRB = 12;         // rows per block
 constexpr int kSchurMaxRows = 255;   // rows per frame (out-degree + 1); larger frames raise ST_BAD_INDEX
 
+// Row list of a depth frame: (pose ix, Ei) first when ix is inside the window, then (pose jj[e], Eij[e]) for its out-edges in CSR
+// order whose target pose is inside the window.  Built by the whole CTA: thread a handles out-edge a, an order-preserving
+// ballot compaction keeps the reference's row order.  Ends with a __syncthreads().
+template <int kThreads>
+__device__ __forceinline__ void build_row_list(const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ edgeidx,
+                                               int e_begin, int deg, int ix, int m, int HW, int t0, int P, const float* __restrict__ Eij,
+                                               const float* __restrict__ Eiin, int* s_pose, const float** s_ptr, int* s_nrows, int* s_wcount) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool self = (ix >= t0 && ix < t0 + P);
+  int pj = -1, e = -1;
+  if (tid < deg && tid < kSchurMaxRows - 1) { e = edgeidx[e_begin + tid]; pj = (int)jj[e] - t0; }
+  const bool keep = (pj >= 0 && pj < P);
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_wcount[warp] = __popc(bal);
+  __syncthreads();
+  int base = self ? 1 : 0;
+  for (int w = 0; w < warp; w++) base += s_wcount[w];
+  if (keep) {
+    const int pos = base + __popc(bal & ((1u << lane) - 1u));
+    s_pose[pos] = pj; s_ptr[pos] = Eij + (size_t)e * 6 * HW;
+  }
+  if (tid == 0) {
+    if (self) { s_pose[0] = ix - t0; s_ptr[0] = Eiin + (size_t)m * 6 * HW; }
+    int tot = self ? 1 : 0;
+    for (int w = 0; w < kThreads / 32; w++) tot += s_wcount[w];
+    *s_nrows = tot;
+    if (deg > kSchurMaxRows - 1) atomicOr(&hdr[HDR_STATUS], ST_BAD_INDEX);
+  }
+  __syncthreads();
+}
+
 template <bool kSingle>
 __global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
     const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
@@ -461,22 +492,10 @@ __global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
   __shared__ int s_pose[kSchurMaxRows + 1];
   __shared__ const float* s_ptr[kSchurMaxRows + 1];
   __shared__ int s_nrows;
+  __shared__ int s_wcount[kSchurThreads / 32];
   extern __shared__ float s_dyn[];
 
-  if (tid == 0) {
-    int c = 0;
-    if (ix >= t0 && ix < t0 + P) { s_pose[c] = ix - t0; s_ptr[c] = Eiin + (size_t)m * 6 * HW; c++; }
-    for (int a = 0; a < deg; a++) {
-      const int e = edgeidx[e_begin + a];
-      const int pj = (int)jj[e] - t0;
-      if (pj >= 0 && pj < P) {
-        if (c < kSchurMaxRows) { s_pose[c] = pj; s_ptr[c] = Eij + (size_t)e * 6 * HW; c++; }
-        else atomicOr(&hdr[HDR_STATUS], ST_BAD_INDEX);
-      }
-    }
-    s_nrows = c;
-  }
-  __syncthreads();
+  build_row_list<kSchurThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
   const int nrows = s_nrows;
   if (nrows == 0) return;
   if (kSingle != (nrows <= kSchurRB)) return;       // the other instantiation owns this frame
@@ -608,6 +627,146 @@ __global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
         } else if (same_row) {
           atomicAdd(&bsys[pa * 6 + (o - 36)], v);
         }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Schur complement for frames with many rows (dense graphs / edge-sharded ranks: out-degree >> 12): SGEMM-style kernel.
+// C = A diag(Q) A^T with A = [6R x pixels].  A CTA computes one 16-row x 16-row tile pair (96 x 96 scalars) for a pixel
+// chunk: thread (ty,tx) owns the 6x6 block pair (row 16*ti+ty, row 16*tj+tx) in registers for the WHOLE chunk (no per-tile
+// reductions), the K loop walks 64-pixel shared-memory tiles stored pixel-major so that a thread reads its 6+6 operands as
+// three 64-bit broadcasts each: 36 FMA per 6 LDS.64.  Tile pairs (ti >= tj) go over blockIdx.z.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSgRows = 16;                 // rows per tile
+constexpr int kSgK = 64;                    // pixels per shared-memory tile
+constexpr int kSgStride = kSgRows * 6 + 2;  // 98 floats per pixel line (even -> 8-byte aligned LDS.64)
+constexpr int kSgThreads = 256;
+
+__global__ void __launch_bounds__(kSgThreads) ba_schur_gemm_kernel(
+    const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
+    const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
+    const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
+    double* __restrict__ Hsys, double* __restrict__ bsys) {
+  const int m = blockIdx.y;
+  if (m >= hdr[HDR_M]) return;
+  const int ix = kx[m];
+  const int e_begin = rowptr[m];
+  const int deg = rowptr[m + 1] - e_begin;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int n = 6 * P;
+
+  __shared__ int s_pose[kSchurMaxRows + 1];
+  __shared__ const float* s_ptr[kSchurMaxRows + 1];
+  __shared__ int s_nrows;
+  __shared__ int s_wcount[kSgThreads / 32];
+  extern __shared__ float sg_dyn[];
+  float* sA = sg_dyn;
+  float* sB = sg_dyn + kSgK * kSgStride;
+  __shared__ float sQw[kSgK];
+  __shared__ float sQ[kSgK];
+
+  build_row_list<kSgThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
+  const int nrows = s_nrows;
+  if (nrows <= kSchurRB) return;                       // small frames belong to ba_schur_kernel<true>
+  const int nT = (nrows + kSgRows - 1) / kSgRows;
+  const int npairs = nT * (nT + 1) / 2;
+  const int px_begin = blockIdx.x * px_per_cta;
+  const int px_end = min(HW, px_begin + px_per_cta);
+  if (px_begin >= px_end) return;
+
+  for (int pr = blockIdx.z; pr < npairs; pr += gridDim.z) {
+    int ti = (int)((sqrtf(8.f * (float)pr + 1.f) - 1.f) * 0.5f);
+    while (ti * (ti + 1) / 2 > pr) ti--;
+    while ((ti + 1) * (ti + 2) / 2 <= pr) ti++;
+    const int tj = pr - ti * (ti + 1) / 2;             // ti >= tj
+    const int ra = min(kSgRows, nrows - ti * kSgRows), rb = min(kSgRows, nrows - tj * kSgRows);
+    const bool diag_tile = (ti == tj);
+    const bool active = (ty < ra) && (tx < rb) && (!diag_tile || ty >= tx);
+    const bool diag_pair = diag_tile && (ty == tx);
+    float acc[36], bacc[6];
+#pragma unroll
+    for (int k = 0; k < 36; k++) acc[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) bacc[k] = 0.f;
+
+    for (int p0 = px_begin; p0 < px_end; p0 += kSgK) {
+      const int np = min(kSgK, px_end - p0);
+      __syncthreads();
+      // ---- stage: A tile scaled by Q, B tile raw; one warp per (row, component) line of 64 pixels, transposed into [px][row*6+c]
+      for (int px = tid; px < kSgK; px += kSgThreads) {
+        const bool okp = px < np;
+        const float q = okp ? 1.0f / __ldg(Cin + (size_t)m * HW + p0 + px) : 0.f;
+        sQ[px] = q;
+        sQw[px] = okp ? __ldg(win + (size_t)m * HW + p0 + px) : 0.f;
+      }
+      __syncthreads();
+      for (int ln = warp; ln < (ra + (diag_tile ? 0 : rb)) * 6; ln += kSgThreads / 32) {
+        const int rowl = ln / 6, c = ln - rowl * 6;
+        const bool second = rowl >= ra;
+        const int row = second ? (tj * kSgRows + rowl - ra) : (ti * kSgRows + rowl);
+        const float* src = s_ptr[row] + (size_t)c * HW + p0;
+        float* dst = (second ? sB : sA) + (second ? rowl - ra : rowl) * 6 + c;
+#pragma unroll
+        for (int h = 0; h < kSgK / 32; h++) {
+          const int px = h * 32 + lane;
+          float v = (px < np) ? __ldg(src + px) : 0.f;
+          if (!second) {
+            // A operand carries Q = 1/C (reference K9: ei = E*q); diagonal tiles keep the unscaled copy in sB
+            if (diag_tile) sB[px * kSgStride + rowl * 6 + c] = v;
+            v *= sQ[px];
+          }
+          dst[px * kSgStride] = v;
+        }
+      }
+      __syncthreads();
+      if (active) {
+        const float* pa = sA + ty * 6;
+        const float* pb = sB + tx * 6;
+#pragma unroll 4
+        for (int px = 0; px < kSgK; px++) {
+          const float2 a01 = *reinterpret_cast<const float2*>(pa + px * kSgStride);
+          const float2 a23 = *reinterpret_cast<const float2*>(pa + px * kSgStride + 2);
+          const float2 a45 = *reinterpret_cast<const float2*>(pa + px * kSgStride + 4);
+          const float2 b01 = *reinterpret_cast<const float2*>(pb + px * kSgStride);
+          const float2 b23 = *reinterpret_cast<const float2*>(pb + px * kSgStride + 2);
+          const float2 b45 = *reinterpret_cast<const float2*>(pb + px * kSgStride + 4);
+          const float ea[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+          const float eb[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+#pragma unroll
+          for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[a * 6 + c] += ea[a] * eb[c];
+          if (diag_pair) {
+            const float w = sQw[px];          // (Q E) w = Q w E
+#pragma unroll
+            for (int c = 0; c < 6; c++) bacc[c] += w * ea[c];
+          }
+        }
+      }
+    }
+    // ---- flush this thread's block pair into the lower triangle
+    if (active) {
+      const int pa_ = s_pose[ti * kSgRows + ty], pb_ = s_pose[tj * kSgRows + tx];
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+          const double v = -(double)acc[a * 6 + c];
+          const int gr = pa_ * 6 + a, gc = pb_ * 6 + c;
+          if (diag_pair) {
+            if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+          } else {
+            if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+            if (gc >= gr) atomicAdd(&Hsys[(size_t)gc * n + gr], v);
+          }
+        }
+      }
+      if (diag_pair) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) atomicAdd(&bsys[pa_ * 6 + a], -(double)bacc[a]);
       }
     }
   }
@@ -792,20 +951,24 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
     // ranks, dense graphs) the block pairs are spread over gridDim.z so the GPU stays full
     const int zsplit = (eff_frames * gx >= 2 * 148) ? 1 : std::min(16, (4 * 148 + eff_frames * gx - 1) / (eff_frames * gx));
     const size_t smem1 = ((size_t)kSchurRB * 6 * kSchurTP + 2 * kSchurTP + (size_t)(kSchurRB * (kSchurRB + 1) / 2) * 42) * sizeof(float);
-    const size_t smem2 = ((size_t)2 * kSchurRB * 6 * kSchurTP + 2 * kSchurTP + (size_t)(kSchurRB * kSchurRB) * 42) * sizeof(float);
+    const size_t smem2 = (size_t)2 * kSgK * kSgStride * sizeof(float);
+    // the SGEMM-style kernel keeps its accumulators in registers over the whole pixel chunk: few long chunks, tile pairs over z
+    const int px_per_cta2 = ((HW + 2) / 3 + kSgK - 1) / kSgK * kSgK;
+    const int gx2 = (HW + px_per_cta2 - 1) / px_per_cta2;
+    const int zsplit2 = std::max(1, std::min(32, (6 * 148 + eff_frames * gx2 - 1) / (eff_frames * gx2)));
     static bool attr_set = false;
     if (!attr_set) {
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur gemm smem attr");
       DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "schur smem attr");
-      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur smem attr");
       attr_set = true;
     }
     ba_schur_kernel<true><<<dim3(gx, a->n_frames, 1), kSchurThreads, smem1, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
                                                            WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
     DBA_CHECK_LAUNCH("ba_schur<single>");
-    ba_schur_kernel<false><<<dim3(gx, a->n_frames, zsplit), kSchurThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
-                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
-                                                            WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+    ba_schur_gemm_kernel<<<dim3(gx2, a->n_frames, zsplit2), kSgThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                                         WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta2, WS(float, L.off_Eij),
+                                                                         WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
     DBA_CHECK_LAUNCH("ba_schur<multi>");
   }
   return DBA_OK;
