@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="f16", choices=["f16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-to-peer reduction inside the solve kernel (default) or a NCCL all-reduce of the pose system")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph (N=1)")
     return ap.parse_args()
 
@@ -162,7 +163,10 @@ def run_ours(args, rank, world, dev):
     sp = ctypes.c_void_p(stream.cuda_stream)
     spbox = [sp]
     engine = sharded.CApiEngine(dev)
-    drv = sharded.ShardedBA(engine)
+    p2p = None
+    if world > 1 and args.collective == "p2p":
+        p2p = sharded.P2PSystem(6 * (pb["t1"] - pb["t0"]), dev)
+    drv = sharded.ShardedBA(engine, p2p=p2p)
 
     def step_resident(ev=None):
         d["poses"].copy_(pristine_poses); d["disps"].copy_(pristine_disps)
@@ -279,7 +283,7 @@ def run_ours(args, rank, world, dev):
         "config": {"workload": "metric: %d edges/GPU x %d GPU(s) over a %d-keyframe window at %dx%d, 4-level r=3 corr_index_forward + ba(itrs=2, lm=1e-4, ep=0.1)"
                                % (EDGES_PER_GPU, world, FRAMES, HT, WD),
                    "edges_this_rank": E, "frames": FRAMES, "depth_frames": pb["M"], "pose_system": 6 * (pb["t1"] - pb["t0"]),
-                   "parallelism": "edge-sharded by source frame, 1 NCCL all-reduce of the %d-double pose system per GN iteration" % (36 * P * P + 6 * P) if world > 1 else "single GPU",
+                   "parallelism": ("edge-sharded by source frame; the %d-double pose system is reduced once per GN iteration, %s" % (36 * P * P + 6 * P, "fused into the Cholesky kernel (peer-to-peer loads over NVLink, release/acquire flags)" if p2p is not None else "NCCL all-reduce")) if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: %.1f GB of correlation volumes stream through the 126 MB L2 every step" % (sum(v.numel() * v.element_size() for v in pb["pyr"]) / 1e9)},
         "e2e": {"value": world * 1e3 / e2e_ms, "unit": "iters/s (512-edge equivalents)", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "droid_backends.corr_index_forward x4 + droid_backends.ba from pinned host buffers; volumes persistent on device"},

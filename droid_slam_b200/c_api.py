@@ -9,7 +9,7 @@ SYMBOLS = [
     "dba_corr_index_forward", "dba_corr_index_backward", "dba_corr_volume_pyramid", "dba_altcorr_forward", "dba_altcorr_backward",
     "dba_projmap", "dba_reproject", "dba_frame_distance", "dba_depth_filter", "dba_iproj",
     "dba_ba_workspace_bytes", "dba_ba_system_offset", "dba_ba_system_bytes",
-    "dba_ba_prepare", "dba_ba_build", "dba_ba_solve", "dba_ba", "dba_ba_read_info",
+    "dba_ba_prepare", "dba_ba_build", "dba_ba_solve", "dba_ba", "dba_ba_read_info", "dba_ba_p2p_signal",
     "dba_solve_workspace_bytes", "dba_solve_spd",
 ]
 
@@ -28,6 +28,7 @@ class BAArgs(ctypes.Structure):
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("stream", ctypes.c_void_p),
         ("own_lo", ctypes.c_int), ("own_hi", ctypes.c_int), ("eta_by_frame", ctypes.c_int),
+        ("p2p_world", ctypes.c_int), ("p2p_rank", ctypes.c_int), ("p2p_epoch", ctypes.c_ulonglong), ("p2p_system", ctypes.c_void_p * 8),
     ]
 
 
@@ -61,7 +62,7 @@ def load():
     L.dba_frame_distance.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, vp]
     L.dba_depth_filter.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, vp]
     L.dba_iproj.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
-    for n in ("dba_ba_prepare", "dba_ba_build", "dba_ba_solve"):
+    for n in ("dba_ba_prepare", "dba_ba_build", "dba_ba_solve", "dba_ba_p2p_signal"):
         getattr(L, n).argtypes = [ctypes.POINTER(BAArgs)]
     L.dba_ba.argtypes = [ctypes.POINTER(BAArgs), ci]
     L.dba_ba_read_info.argtypes = [ctypes.POINTER(BAArgs), ctypes.POINTER(ci), ctypes.POINTER(ci)]

@@ -898,6 +898,7 @@ static int check_ba_args(const dba_ba_args* a, Layout& L) {
   DBA_CHECK_ARG(a->motion_only || (a->eta && a->eta_rows >= 1), "eta missing");
   DBA_CHECK_ARG(a->motion_only || !a->eta_by_frame || a->eta_rows >= a->n_frames, "eta_by_frame needs one eta row per frame");
   DBA_CHECK_ARG(a->own_lo >= 0 && a->own_hi >= a->own_lo, "bad ownership range");
+  DBA_CHECK_ARG(a->p2p_world <= 8 && (a->p2p_world <= 1 || (a->p2p_rank >= 0 && a->p2p_rank < a->p2p_world)), "bad p2p rank/world");
   DBA_CHECK_ARG(a->workspace != nullptr, "null workspace");
   DBA_CHECK_ARG(a->n_frames <= 65535, "more than 65535 frames");
   L = make_layout(a->n_frames, a->n_edges, a->ht, a->wd, a->t0, a->t1);
@@ -906,6 +907,13 @@ static int check_ba_args(const dba_ba_args* a, Layout& L) {
 }
 
 #define WS(T, off) reinterpret_cast<T*>(reinterpret_cast<char*>(a->workspace) + (off))
+
+// where the reduced pose system of this Gauss-Newton iteration is accumulated: the private workspace, or -- for the fused
+// peer-to-peer reduction -- slot (epoch & 1) of this rank's peer-visible buffer
+static double* system_ptr(const dba_ba_args* a, const Layout& L) {
+  if (a->p2p_world > 1) return reinterpret_cast<double*>(a->p2p_system[a->p2p_rank]) + (size_t)(a->p2p_epoch & 1ull) * ((size_t)L.n * L.n + L.n);
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(a->workspace) + L.off_sys);
+}
 
 extern "C" int dba_ba_prepare(const dba_ba_args* a) {
   Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
@@ -925,10 +933,11 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
   Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)a->stream;
   const int HW = a->ht * a->wd;
-  DBA_CHECK_CUDA(cudaMemsetAsync(WS(char, L.off_sys), 0, ((size_t)L.n * L.n + L.n) * sizeof(double), st), "ba_build memset");
-  if (L.P == 0) return DBA_OK;
-  double* Hsys = WS(double, L.off_sys);
+  double* Hsys = system_ptr(a, L);
   double* bsys = Hsys + (size_t)L.n * L.n;
+  DBA_CHECK_CUDA(cudaMemsetAsync(Hsys, 0, ((size_t)L.n * L.n + L.n) * sizeof(double), st), "ba_build memset");
+  DBA_CHECK_CUDA(cudaMemsetAsync(WS(int, L.off_hdr) + HDR_CHOL_FAIL, 0, sizeof(int), st), "ba_build memset");
+  if (L.P == 0) return DBA_OK;
   // frames that can own edges on this rank (edge-sharded runs own a sub-range): size the pixel chunks so the grid fills the GPU
   const int eff_frames = std::max(1, std::min(a->n_frames, a->own_hi - a->own_lo));
   const int ppt = (eff_frames * ((HW + 4 * kBuildThreads - 1) / (4 * kBuildThreads)) >= 148) ? 4
@@ -979,11 +988,19 @@ extern "C" int dba_ba_solve(const dba_ba_args* a) {
   if (L.P == 0) return DBA_OK;
   cudaStream_t st = (cudaStream_t)a->stream;
   const int HW = a->ht * a->wd;
-  double* Hsys = WS(double, L.off_sys);
+  double* Hsys = system_ptr(a, L);
   double* bsys = Hsys + (size_t)L.n * L.n;
   float* dx = WS(float, L.off_dx);
   {
-    int rc2 = chol_solve_launch(Hsys, bsys, L.n, (double)a->lm, (double)a->ep, WS(void, L.off_L), WS(int, L.off_hdr) + HDR_CHOL_FAIL, dx, st);
+    CholPeers peers; peers.world = 0;
+    if (a->p2p_world > 1) {
+      const size_t nd = (size_t)L.n * L.n + L.n;
+      peers.world = a->p2p_world; peers.epoch = a->p2p_epoch;
+      for (int k = 0; k < a->p2p_world; k++) peers.sys[k] = reinterpret_cast<const double*>(a->p2p_system[k]) + (size_t)(a->p2p_epoch & 1ull) * nd;
+      peers.flags = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const double*>(a->p2p_system[a->p2p_rank]) + 2 * nd);
+    }
+    int rc2 = chol_solve_launch(Hsys, bsys, L.n, (double)a->lm, (double)a->ep, WS(void, L.off_L), WS(int, L.off_hdr) + HDR_CHOL_FAIL, dx, st,
+                                a->p2p_world > 1 ? &peers : nullptr);
     if (rc2) return rc2;
   }
   if (!a->motion_only) {
@@ -996,6 +1013,28 @@ extern "C" int dba_ba_solve(const dba_ba_args* a) {
   }
   ba_pose_retr_kernel<<<(L.P + 127) / 128, 128, 0, st>>>(a->poses, dx, a->t0, L.P, a->dx_out, WS(int, L.off_hdr));
   DBA_CHECK_LAUNCH("ba_pose_retr");
+  return DBA_OK;
+}
+
+// publish this rank's partial system to every peer: release stores of the epoch into flags[rank] of each peer's buffer
+namespace dba {
+struct P2PSignal { unsigned long long* flag[8]; int world; unsigned long long epoch; };
+__global__ void ba_p2p_signal_kernel2(P2PSignal s) {
+  __threadfence_system();
+  const int lane = threadIdx.x;
+  if (lane < s.world) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.flag[lane]), "l"(s.epoch) : "memory");
+}
+}  // namespace dba
+
+extern "C" int dba_ba_p2p_signal(const dba_ba_args* a) {
+  Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
+  if (a->p2p_world <= 1) return DBA_OK;
+  const size_t nd = (size_t)L.n * L.n + L.n;
+  dba::P2PSignal s; s.world = a->p2p_world; s.epoch = a->p2p_epoch;
+  for (int k = 0; k < a->p2p_world; k++)
+    s.flag[k] = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(a->p2p_system[k]) + 2 * nd) + a->p2p_rank;
+  dba::ba_p2p_signal_kernel2<<<1, 32, 0, (cudaStream_t)a->stream>>>(s);
+  DBA_CHECK_LAUNCH("ba_p2p_signal");
   return DBA_OK;
 }
 

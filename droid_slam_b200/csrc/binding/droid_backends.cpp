@@ -81,6 +81,7 @@ std::vector<torch::Tensor> ba(torch::Tensor poses, torch::Tensor disps, torch::T
   a.dx_out = dx.data_ptr<float>(); a.dz_out = nullptr;
   a.workspace = ws.data_ptr(); a.workspace_bytes = ws_bytes; a.stream = cur_stream();
   a.own_lo = 0; a.own_hi = n_frames; a.eta_by_frame = 0;
+  a.p2p_world = 0; a.p2p_rank = 0; a.p2p_epoch = 0; for (int k = 0; k < 8; k++) a.p2p_system[k] = nullptr;
 
   torch::Tensor dz;
   if (!motion_only) {

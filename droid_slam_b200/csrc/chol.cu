@@ -82,6 +82,7 @@ struct CholParams {
   int n, nt;
   double lm, ep;
   unsigned long long* timing;   // debug (DBA_CHOL_TIMING=1): globaltimer stamps of CTA 0 / the potrf warp, else nullptr
+  CholPeers peers;              // world <= 1: plain local system
 };
 
 // one warp: C (32x32 at Ct) -= A (at At) * B^T (at Bt); lane (rg = lane>>3, cg = lane&7) owns rows 8rg..8rg+7, cols 4cg..4cg+3
@@ -139,22 +140,52 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
   double (*s_D)[kTP] = reinterpret_cast<double (*)[kTP]>(s_dyn + (size_t)2 * kCholWarps * kT * kTP);
   double (*s_T)[kTP] = reinterpret_cast<double (*)[kTP]>(s_dyn + (size_t)2 * kCholWarps * kT * kTP + kT * kTP);
 
+  // ---- fused peer-to-peer reduction: wait until every rank has published its partial system for this epoch ------------
+  const int world = p.peers.world;
+  if (world > 1) {
+    __shared__ int s_timeout;
+    if (tid == 0) {
+      int bad = 0;
+      for (int r = 0; r < world; r++) {
+        unsigned long long v = 0;
+        long long spins = 0;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.peers.flags + r) : "memory");
+        } while (v < p.peers.epoch && ++spins < (1ll << 24));
+        if (v < p.peers.epoch) bad = 1;
+      }
+      s_timeout = bad;
+    }
+    __syncthreads();
+    if (cta == 0 && tid == 0) *p.fail = s_timeout ? 2 : 0;   // a peer never arrived: give up loudly (dx = 0), never hang
+  } else if (cta == 0 && tid == 0) *p.fail = 0;
   // ---- load: lower tiles of H with damping (reference :1205-1206), identity padding, rhs row ------------------
   {
     const size_t total = (size_t)(nt + 1) * kT * ld;
+    const size_t nn = (size_t)n * n;
     for (size_t idx = (size_t)cta * kCholThreads + tid; idx < total; idx += (size_t)ncta * kCholThreads) {
       const int r = (int)(idx / ld), c = (int)(idx - (size_t)r * ld);
       double v = 0.0;
+      size_t src = (size_t)-1;                          // element of the [n*n | n] system feeding this entry
       if (r < nt * kT) {
         if (r < n && c < n) {
-          if (c <= r) { v = p.H[(size_t)r * n + c]; if (r == c) v += p.ep + p.lm * v; }
-          else if ((r >> 5) == (c >> 5)) v = p.H[(size_t)c * n + r];     // diagonal tiles are kept fully symmetric
+          if (c <= r) src = (size_t)r * n + c;
+          else if ((r >> 5) == (c >> 5)) src = (size_t)c * n + r;     // diagonal tiles are kept fully symmetric
         } else if (r == c) v = 1.0;
-      } else if (r == nt * kT && c < n) v = p.b[c];
+      } else if (r == nt * kT && c < n) src = nn + c;
+      if (src != (size_t)-1) {
+        if (world > 1) {
+          for (int q = 0; q < world; q++) {             // fixed rank order: every rank computes the identical sum
+            double t;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t) : "l"(p.peers.sys[q] + src) : "memory");
+            v += t;
+          }
+        } else v = (src < nn) ? p.H[src] : p.b[src - nn];
+        if (src < nn && r == c) v += p.ep + p.lm * v;
+      }
       stcg(L + idx, v);
     }
   }
-  if (cta == 0 && tid == 0) *p.fail = 0;
   CHOL_STAMP(0);
   cluster.sync();
   CHOL_STAMP(1);
@@ -324,10 +355,12 @@ size_t chol_workspace_bytes(int n) {
 }
 
 // H [n][n] fp64, b [n] fp64 -> x [n] fp32; fail flag is a device int
-int chol_solve_launch(const double* H, const double* b, int n, double lm, double ep, void* workspace, int* fail, float* x, cudaStream_t st) {
+int chol_solve_launch(const double* H, const double* b, int n, double lm, double ep, void* workspace, int* fail, float* x, cudaStream_t st,
+                      const CholPeers* peers) {
   if (n <= 0) return DBA_OK;
   CholParams p;
   p.H = H; p.b = b; p.n = n; p.nt = (n + kT - 1) / kT; p.lm = lm; p.ep = ep; p.fail = fail; p.x = x;
+  if (peers) p.peers = *peers; else { p.peers.world = 0; p.peers.flags = nullptr; p.peers.epoch = 0; for (int k = 0; k < 8; k++) p.peers.sys[k] = nullptr; }
   const size_t ld = (size_t)p.nt * kT;
   p.L = reinterpret_cast<double*>(workspace);
   p.Linv = p.L + (size_t)(p.nt + 1) * kT * ld;

@@ -12,7 +12,14 @@ namespace dba {
 void set_error(const char* fmt, ...);
 // chol.cu: damped SPD solve (fp64, one thread-block cluster)
 size_t chol_workspace_bytes(int n);
-int chol_solve_launch(const double* H, const double* b, int n, double lm, double ep, void* workspace, int* fail, float* x, cudaStream_t st);
+struct CholPeers {            // fused peer-to-peer reduction (world > 1): H/b are summed over peer copies in rank order
+  int world;
+  const double* sys[8];       // peer-mapped pointers to each rank's [n*n + n] system for this epoch
+  const unsigned long long* flags;   // this rank's flag array [world], flag[p] >= epoch when rank p has published
+  unsigned long long epoch;
+};
+int chol_solve_launch(const double* H, const double* b, int n, double lm, double ep, void* workspace, int* fail, float* x, cudaStream_t st,
+                      const CholPeers* peers = nullptr);
 int cuda_fail(cudaError_t e, const char* what);
 
 #define DBA_CHECK_ARG(cond, msg)                                   \

@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 from . import c_api
 
-__all__ = ["partition_frames", "shard_edges", "CApiEngine", "ShardedBA"]
+__all__ = ["partition_frames", "shard_edges", "CApiEngine", "ShardedBA", "P2PSystem"]
 
 
 def partition_frames(ii, n_frames, world):
@@ -39,6 +39,25 @@ def shard_edges(ii, lo, hi):
     return torch.nonzero((ii >= lo) & (ii < hi)).reshape(-1)
 
 
+class P2PSystem:
+    """peer-visible buffers for the fused reduction of the pose system: every rank allocates two slots of
+    36P^2+6P doubles plus 8 flags in symmetric memory (torch.distributed._symmetric_memory) and learns its peers' mapped pointers"""
+
+    def __init__(self, n, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.nd = n * n + n
+        self.buf = symm_mem.empty(2 * self.nd + 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.world = int(self.hdl.world_size)
+        self.rank = int(self.hdl.rank)
+        self.epoch = 0
+        assert self.world <= 8
+
+
 class CApiEngine:
     """the three phases of the C ABI (include/droid_b200.h) on one GPU"""
 
@@ -47,7 +66,7 @@ class CApiEngine:
         self.device = torch.device(device)
         self.args = None
 
-    def setup(self, poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj, t0, t1, lm, ep, own):
+    def setup(self, poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj, t0, t1, lm, ep, own, p2p=None):
         N, ht, wd = disps.shape
         E = ii.shape[0]
         L = self.L
@@ -70,13 +89,26 @@ class CApiEngine:
         a.workspace, a.workspace_bytes = self.ws.data_ptr(), self.ws_bytes
         a.stream = torch.cuda.current_stream(self.device).cuda_stream
         a.own_lo, a.own_hi = own
+        self.p2p = p2p
+        if p2p is not None:
+            assert p2p.nd == n * n + n, "P2PSystem was sized for another window"
+            a.p2p_world, a.p2p_rank = p2p.world, p2p.rank
+            for k, ptr in enumerate(p2p.ptrs):
+                a.p2p_system[k] = ptr
         self.args = a
         self._keep = (poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj)
         c_api.check(L.dba_ba_prepare(ctypes.byref(a)), "ba_prepare")
 
     def build(self):
+        if self.p2p is not None:          # next epoch on every rank: selects the slot and is what the peers wait for
+            self.p2p.epoch += 1
+            self.args.p2p_epoch = self.p2p.epoch
         c_api.check(self.L.dba_ba_build(ctypes.byref(self.args)), "ba_build")
         return self.system
+
+    def publish(self):
+        """fused path: release-store this rank's epoch into every peer's flag array (after build, before solve)"""
+        c_api.check(self.L.dba_ba_p2p_signal(ctypes.byref(self.args)), "ba_p2p_signal")
 
     def solve(self):
         c_api.check(self.L.dba_ba_solve(ctypes.byref(self.args)), "ba_solve")
@@ -85,9 +117,10 @@ class CApiEngine:
 class ShardedBA:
     """host-side driver of an edge-sharded BA; `engine` provides setup/build/solve for the local shard"""
 
-    def __init__(self, engine, group=None):
+    def __init__(self, engine, group=None, p2p=None):
         self.engine = engine
         self.group = group
+        self.p2p = p2p          # P2PSystem: fuse the all-reduce into the Cholesky kernel's load phase over NVLink peer memory
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.allreduce_bytes = 0
@@ -97,22 +130,26 @@ class ShardedBA:
         """poses/disps are the full (replicated) state; targets/weights/ii/jj are this rank's edge shard.
         In place on poses (all ranks identical) and disps (owned frames; all frames after the final exchange)."""
         own = bounds[self.rank]
-        if exchange_disps and self.world > 1:
-            self._disps_before = disps.clone()
-        self.engine.setup(poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj, t0, t1, lm, ep, own)
+        if self.p2p is not None:
+            self.engine.setup(poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj, t0, t1, lm, ep, own, p2p=self.p2p)
+        else:
+            self.engine.setup(poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj, t0, t1, lm, ep, own)
         self.allreduce_bytes = 0
         for _ in range(iterations):
             system = self.engine.build()
-            if self.world > 1:
+            if self.p2p is not None:
+                self.engine.publish()                 # no collective call: the solve kernel sums the peers' copies itself
+            elif self.world > 1:
                 dist.all_reduce(system, op=dist.ReduceOp.SUM, group=self.group)     # the one exchange per GN iteration
                 self.allreduce_bytes += system.numel() * system.element_size()
             self.engine.solve()
         if exchange_disps and self.world > 1:
-            # owners' inverse depths: ONE all-reduce of the owner-masked delta instead of one broadcast per rank
+            # owners' inverse depths: during the iterations a rank only reads and writes the rows it owns, so the other rows can be
+            # zeroed and ONE all-reduce (sum) rebuilds the full tensor in place on every rank
             lo, hi = own
-            delta = torch.zeros_like(disps)
-            if hi > lo:
-                delta[lo:hi] = disps[lo:hi] - self._disps_before[lo:hi]
-            dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.group)
-            disps.copy_(self._disps_before + delta)
+            if lo > 0:
+                disps[:lo].zero_()
+            if hi < disps.shape[0]:
+                disps[hi:].zero_()
+            dist.all_reduce(disps, op=dist.ReduceOp.SUM, group=self.group)
         return poses, disps

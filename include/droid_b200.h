@@ -130,12 +130,22 @@ typedef struct {
    * rest); single-GPU callers pass own_lo = 0, own_hi = n_frames.  eta_by_frame != 0: eta has n_frames rows indexed by
    * FRAME id instead of M rows in depth-frame order (a rank's local depth-frame set differs from the global one). */
   int own_lo, own_hi, eta_by_frame;
+  /* optional fused peer-to-peer reduction of the pose system over NVLink peer memory (p2p_world > 1), replacing the separate
+   * all-reduce: the rank accumulates its partial system in p2p_system[p2p_rank] (slot p2p_epoch & 1 of two, each 36P^2+6P
+   * doubles; 8 uint64 flags follow the two slots), dba_ba_p2p_signal() publishes it with release stores into every peer's
+   * flags[p2p_rank], and the Cholesky kernel of dba_ba_solve waits for the W flags and sums the W peer copies in rank order
+   * (bit-identical on every rank) straight out of peer memory.  p2p_system[] are peer-mapped device pointers (e.g. from
+   * torch.distributed._symmetric_memory); p2p_epoch must increase by one per Gauss-Newton iteration on every rank. */
+  int p2p_world, p2p_rank;
+  unsigned long long p2p_epoch;
+  void* p2p_system[8];
 } dba_ba_args;
 
 int dba_ba_prepare(const dba_ba_args* a);
 int dba_ba_build(const dba_ba_args* a);
 int dba_ba_solve(const dba_ba_args* a);
 int dba_ba(const dba_ba_args* a, int iterations);
+int dba_ba_p2p_signal(const dba_ba_args* a);   /* after dba_ba_build, before dba_ba_solve, when p2p_world > 1 */
 /* synchronises `stream` and reads back M = number of depth frames found by the last dba_ba_prepare on this
  * workspace and the sticky device status word (0 = ok, bit0 = index out of range, bit1 = eta rows != M,
  * bit2 = Cholesky hit a non-positive pivot in some iteration -> that iteration's dx = 0 like the reference). */
