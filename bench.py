@@ -187,9 +187,10 @@ def run_ours(args, rank, world, dev):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
-    # N=1: the whole step (4 lookups + prepare + 2 x (build, Schur, Cholesky, back-substitution, retraction)) is a static launch
-    # sequence with no host synchronisation, so it is captured once into a CUDA graph and replayed (the C ABI is capture-safe)
-    use_graph = (world == 1) and not args.no_graph
+    # the whole step (4 lookups + prepare + 2 x (build, Schur, [publish,] Cholesky, back-substitution, retraction) [+ depth exchange])
+    # is a static launch sequence with no host synchronisation, so it is captured once into a CUDA graph and replayed (the C ABI is
+    # capture-safe; for N > 1 the peer-to-peer epoch lives on the device and NCCL's depth all-reduce is captured with the rest)
+    use_graph = not args.no_graph and BA_ITERS % 2 == 0
     graph = None
     if use_graph:
         side = torch.cuda.Stream()
@@ -279,12 +280,12 @@ def run_ours(args, rank, world, dev):
         return float(t[0]) / args.steps
 
     e2e_eager_ms = time_e2e(step_e2e)
-    copy_only_ms = time_e2e(lambda: [pin[k].to(dev, non_blocking=True) for k in pin if k != "eta_by_frame"])     # PCIe share of the step
+    copy_only_ms = time_e2e(lambda: [pin[k].to(dev, non_blocking=True) for k in pin if k != ("eta_by_frame" if world == 1 else "eta")])     # PCIe share of the step
     e2e_ms, e2e_mode = e2e_eager_ms, "eager"
     if use_graph:
         # the same calls captured once: pinned-host -> device copies, the four lookups, ba and the device -> pinned-host reads are all
         # nodes of one CUDA graph (the copies of the BA inputs form a parallel branch), so a step is a single graph launch
-        stat = {k: torch.empty_like(pin[k], device=dev) for k in pin if k != "eta_by_frame"}
+        stat = {k: torch.empty_like(pin[k], device=dev) for k in pin if k != ("eta_by_frame" if world == 1 else "eta")}
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         e2e_graph = torch.cuda.CUDAGraph()
@@ -298,8 +299,13 @@ def run_ours(args, rank, world, dev):
                         stat[k].copy_(pin[k], non_blocking=True)
             keep = [be.corr_index_forward(pb["pyr"][l], stat["coords"] / 2 ** l, RADIUS)[0] for l in range(LEVELS)]
             main.wait_stream(copy_stream)
-            dx, dz = be.ba(stat["poses"], stat["disps"], stat["intrinsics"], stat["disps_sens"], stat["targets"], stat["weights"], stat["eta"],
-                           stat["ii"], stat["jj"], pb["t0"], pb["t1"], BA_ITERS, LM, EP, False)
+            if world == 1:
+                dx, dz = be.ba(stat["poses"], stat["disps"], stat["intrinsics"], stat["disps_sens"], stat["targets"], stat["weights"], stat["eta"],
+                               stat["ii"], stat["jj"], pb["t0"], pb["t1"], BA_ITERS, LM, EP, False)
+            else:
+                drv.run(stat["poses"], stat["disps"], stat["intrinsics"], stat["disps_sens"], stat["targets"], stat["weights"], stat["eta_by_frame"],
+                        stat["ii"], stat["jj"], pb["t0"], pb["t1"], BA_ITERS, LM, EP, pb["bounds"], exchange_disps=True)
+                dx = engine.dx
             out_pin["poses"].copy_(stat["poses"], non_blocking=True); out_pin["disps"].copy_(stat["disps"], non_blocking=True)
             out_pin["dx"].copy_(dx, non_blocking=True)
         torch.cuda.current_stream().wait_stream(side)

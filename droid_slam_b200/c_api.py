@@ -28,7 +28,7 @@ class BAArgs(ctypes.Structure):
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("stream", ctypes.c_void_p),
         ("own_lo", ctypes.c_int), ("own_hi", ctypes.c_int), ("eta_by_frame", ctypes.c_int),
-        ("p2p_world", ctypes.c_int), ("p2p_rank", ctypes.c_int), ("p2p_epoch", ctypes.c_ulonglong), ("p2p_system", ctypes.c_void_p * 8),
+        ("p2p_world", ctypes.c_int), ("p2p_rank", ctypes.c_int), ("p2p_epoch", ctypes.c_ulonglong), ("p2p_system", ctypes.c_void_p * 8), ("p2p_epoch_dev", ctypes.c_void_p),
     ]
 
 

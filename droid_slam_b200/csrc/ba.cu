@@ -19,6 +19,7 @@
 //   * back-substitution dz = Q (w - E^T dx) keeps the reference quirk Q9 (rows whose pose index is <= 0 are skipped,
 //     src/droid_kernels.cu:1114), then retraction of poses (left-multiplicative Exp, no renormalisation) and disps.
 #include "common.cuh"
+#include "tcgen05.cuh"
 #include <math.h>
 #include <algorithm>
 
@@ -431,17 +432,10 @@ __global__ void __launch_bounds__(kBuildThreads, 2) ba_build_kernel(
 // Schur complement:  Hsys -= sum_k E_k Q_k E_k^T ,  bsys -= sum_k E_k Q_k w_k       (reference K9/K10 + schur_block)
 // rows of frame k: (pose k, Ei_k) if k is in [t0,t1), then (pose jj[e], Eij[e]) for the out-edges e of k; rows whose pose
 // is outside [t0,t1) are dropped (they contribute nothing, reference :1155,:1257).
-// One CTA per (frame, pixel chunk).  The rows are staged tile by tile (256 pixels) into shared memory with 128-bit
-// coalesced loads; a WARP owns a 6x6 block pair (r <= r'), its lanes split the pixels of the tile, the 36(+6) partial sums
-// are combined with a transpose-reduction (31 shuffles for 32 values) into a shared accumulator that the pair's owner
-// alone touches (no atomics, deterministic), and the CTA flushes its block pairs once with fp64 atomics into the LOWER
-// triangle of the reduced system.  kSingle: all rows fit one 12-row block (86 KB smem, 2 CTAs/SM); otherwise the
-// frame is processed as pairs of row blocks.
+// Two kernels share the work: ba_schur_small_kernel (frames with <= 16 rows, the usual case) and ba_schur_gemm_kernel (more rows:
+// dense graphs, edge-sharded ranks).  Both keep 6x6 block pairs in registers over a whole pixel chunk, accumulate in fp32 like the
+// reference and flush once with fp64 atomics into the LOWER triangle of the reduced system.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSchurThreads = 256;
-constexpr int kSchurWarps = kSchurThreads / 32;
-constexpr int kSchurTP = 256;        // pixels per shared-memory tile
-constexpr int kSchurRB = 12;         // rows per block
 constexpr int kSchurMaxRows = 255;   // rows per frame (out-degree + 1); larger frames raise ST_BAD_INDEX
 
 // Row list of a depth frame: (pose ix, Ei) first when ix is inside the window, then (pose jj[e], Eij[e]) for its out-edges in CSR
@@ -475,163 +469,6 @@ __device__ __forceinline__ void build_row_list(const int64_t* __restrict__ jj, i
   __syncthreads();
 }
 
-template <bool kSingle>
-__global__ void __launch_bounds__(kSchurThreads) ba_schur_kernel(
-    const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
-    const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
-    const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
-    double* __restrict__ Hsys, double* __restrict__ bsys) {
-  const int m = blockIdx.y;
-  if (m >= hdr[HDR_M]) return;
-  const int ix = kx[m];
-  const int e_begin = rowptr[m];
-  const int deg = rowptr[m + 1] - e_begin;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = 6 * P;
-
-  __shared__ int s_pose[kSchurMaxRows + 1];
-  __shared__ const float* s_ptr[kSchurMaxRows + 1];
-  __shared__ int s_nrows;
-  __shared__ int s_wcount[kSchurThreads / 32];
-  extern __shared__ float s_dyn[];
-
-  build_row_list<kSchurThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
-  const int nrows = s_nrows;
-  if (nrows == 0) return;
-  if (kSingle != (nrows <= kSchurRB)) return;       // the other instantiation owns this frame
-
-  const int nblk = (nrows + kSchurRB - 1) / kSchurRB;
-  constexpr int kRowFloats = 6 * kSchurTP;           // one row of a tile: [6][TP]
-  float* sA = s_dyn;                                  // [RB][6][TP]
-  float* sB = kSingle ? sA : sA + kSchurRB * kRowFloats;
-  float* sQ = (kSingle ? sA + kSchurRB * kRowFloats : sB + kSchurRB * kRowFloats);
-  float* sQw = sQ + kSchurTP;
-  float* sS = sQw + kSchurTP;                         // [pairs][42]: 36 block entries + 6 rhs entries
-  const int px_begin = blockIdx.x * px_per_cta;
-  const int px_end = min(HW, px_begin + px_per_cta);
-  if (px_begin >= px_end) return;
-  const bool vec4 = (HW % 4) == 0;
-
-  int pair_id = 0;
-  for (int bi = 0; bi < nblk; bi++) {
-    for (int bj = bi; bj < nblk; bj++, pair_id++) {
-      if ((pair_id % (int)gridDim.z) != (int)blockIdx.z) continue;        // block pairs are spread over gridDim.z CTAs
-      const int ra = min(kSchurRB, nrows - bi * kSchurRB);
-      const int rb = min(kSchurRB, nrows - bj * kSchurRB);
-      const int npairs = (bi == bj) ? ra * (ra + 1) / 2 : ra * rb;
-      __syncthreads();
-      for (int k = tid; k < npairs * 42; k += kSchurThreads) sS[k] = 0.f;
-
-      for (int p0 = px_begin; p0 < px_end; p0 += kSchurTP) {
-        const int np = min(kSchurTP, px_end - p0);
-        __syncthreads();
-        // ---- stage the rows of block bi (and bj): one warp per (row, component) line of 256 pixels
-        const int nlines = (ra + ((bi == bj) ? 0 : rb)) * 6;
-        for (int ln = warp; ln < nlines; ln += kSchurWarps) {
-          const int rowl = ln / 6, c = ln - rowl * 6;
-          const bool second = rowl >= ra;
-          const int row = second ? (bj * kSchurRB + rowl - ra) : (bi * kSchurRB + rowl);
-          float* dst = (second ? sB + (rowl - ra) * kRowFloats : sA + rowl * kRowFloats) + c * kSchurTP;
-          const float* src = s_ptr[row] + (size_t)c * HW + p0;
-          if (vec4 && np == kSchurTP) {
-#pragma unroll
-            for (int h = 0; h < kSchurTP / 128; h++) {
-              const float4 v = __ldg(reinterpret_cast<const float4*>(src) + h * 32 + lane);
-              reinterpret_cast<float4*>(dst)[h * 32 + lane] = v;
-            }
-          } else {
-            for (int px = lane; px < kSchurTP; px += 32) dst[px] = (px < np) ? __ldg(src + px) : 0.f;
-          }
-        }
-        for (int px = tid; px < kSchurTP; px += kSchurThreads) {
-          float q = 0.f, qw = 0.f;
-          if (px < np) { q = 1.0f / __ldg(Cin + (size_t)m * HW + p0 + px); qw = q * __ldg(win + (size_t)m * HW + p0 + px); }
-          sQ[px] = q; sQw[px] = qw;
-        }
-        __syncthreads();
-        // ---- block pairs: one warp per pair, lanes split the pixels
-        for (int pr = warp; pr < npairs; pr += kSchurWarps) {
-          int r, r2;
-          if (bi == bj) {
-            r2 = (int)((sqrtf(8.f * (float)pr + 1.f) - 1.f) * 0.5f);
-            while (r2 * (r2 + 1) / 2 > pr) r2--;
-            while ((r2 + 1) * (r2 + 2) / 2 <= pr) r2++;
-            r = pr - r2 * (r2 + 1) / 2;
-          } else { r = pr / rb; r2 = pr - r * rb; }
-          const float* rowA = sA + r * kRowFloats;
-          const float* rowB = ((bi == bj) ? sA : sB) + r2 * kRowFloats;
-          const bool diag = (bi == bj) && (r == r2);
-          float acc[36], bacc[6];
-#pragma unroll
-          for (int k = 0; k < 36; k++) acc[k] = 0.f;
-#pragma unroll
-          for (int k = 0; k < 6; k++) bacc[k] = 0.f;
-#pragma unroll 2
-          for (int px = lane; px < kSchurTP; px += 32) {
-            const float q = sQ[px];
-            float ea[6], eb[6];
-#pragma unroll
-            for (int c = 0; c < 6; c++) { ea[c] = rowA[c * kSchurTP + px]; eb[c] = rowB[c * kSchurTP + px]; }
-            if (diag) {
-              const float qw = sQw[px];
-#pragma unroll
-              for (int c = 0; c < 6; c++) bacc[c] += qw * ea[c];
-            }
-#pragma unroll
-            for (int a = 0; a < 6; a++) {
-              const float eq = ea[a] * q;             // ei[n] = E*q   (reference :1039)
-#pragma unroll
-              for (int c = 0; c < 6; c++) acc[a * 6 + c] += eq * eb[c];
-            }
-          }
-          // combine the lanes: values 0..31 by transpose-reduction, 32..35 (+ rhs) by butterflies
-          float v32[32];
-#pragma unroll
-          for (int k = 0; k < 32; k++) v32[k] = acc[k];
-          const float tot = transpose_reduce32(v32, lane);
-          float* dstS = sS + pr * 42;
-          dstS[lane] += tot;
-          float t4[4] = {warp_sum(acc[32]), warp_sum(acc[33]), warp_sum(acc[34]), warp_sum(acc[35])};
-          if (lane < 4) dstS[32 + lane] += (lane == 0) ? t4[0] : (lane == 1) ? t4[1] : (lane == 2) ? t4[2] : t4[3];
-          if (diag) {
-            float t6[6];
-#pragma unroll
-            for (int c = 0; c < 6; c++) t6[c] = warp_sum(bacc[c]);
-            if (lane < 6) dstS[36 + lane] += (lane == 0) ? t6[0] : (lane == 1) ? t6[1] : (lane == 2) ? t6[2] : (lane == 3) ? t6[3] : (lane == 4) ? t6[4] : t6[5];
-          }
-        }
-      }
-      __syncthreads();
-      // ---- flush: lower triangle of the reduced system
-      for (int k = tid; k < npairs * 42; k += kSchurThreads) {
-        const int pr = k / 42, o = k - pr * 42;
-        int r, r2;
-        if (bi == bj) {
-          r2 = (int)((sqrtf(8.f * (float)pr + 1.f) - 1.f) * 0.5f);
-          while (r2 * (r2 + 1) / 2 > pr) r2--;
-          while ((r2 + 1) * (r2 + 2) / 2 <= pr) r2++;
-          r = pr - r2 * (r2 + 1) / 2;
-        } else { r = pr / rb; r2 = pr - r * rb; }
-        const int pa = s_pose[bi * kSchurRB + r], pb = s_pose[bj * kSchurRB + r2];
-        const bool same_row = (bi == bj) && (r == r2);
-        const double v = -(double)sS[k];
-        if (o < 36) {
-          const int a = o / 6, c = o - a * 6;
-          const int gr = pa * 6 + a, gc = pb * 6 + c;       // S block (pa,pb)[a][c]; its transpose sits at (pb,pa)[c][a]
-          if (same_row) {
-            if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
-          } else {
-            if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
-            if (gc >= gr) atomicAdd(&Hsys[(size_t)gc * n + gr], v);
-          }
-        } else if (same_row) {
-          atomicAdd(&bsys[pa * 6 + (o - 36)], v);
-        }
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Schur complement for frames with many rows (dense graphs / edge-sharded ranks: out-degree >> 12): SGEMM-style kernel.
 // C = A diag(Q) A^T with A = [6R x pixels].  A CTA computes one 16-row x 16-row tile pair (96 x 96 scalars) for a pixel
@@ -646,7 +483,7 @@ constexpr int kSgThreads = 256;
 
 __global__ void __launch_bounds__(kSgThreads) ba_schur_gemm_kernel(
     const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
-    const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
+    const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta, int min_rows,
     const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
     double* __restrict__ Hsys, double* __restrict__ bsys) {
   const int m = blockIdx.y;
@@ -670,7 +507,7 @@ __global__ void __launch_bounds__(kSgThreads) ba_schur_gemm_kernel(
 
   build_row_list<kSgThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
   const int nrows = s_nrows;
-  if (nrows <= kSchurRB) return;                       // small frames belong to ba_schur_kernel<true>
+  if (nrows <= min_rows) return;                       // smaller frames belong to ba_schur_tc_kernel / ba_schur_small_kernel
   const int nT = (nrows + kSgRows - 1) / kSgRows;
   const int npairs = nT * (nT + 1) / 2;
   const int px_begin = blockIdx.x * px_per_cta;
@@ -770,6 +607,400 @@ __global__ void __launch_bounds__(kSgThreads) ba_schur_gemm_kernel(
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Schur complement for frames with at most 16 rows (the usual case: out-degree + 1): the same register-resident 6x6 block pairs
+// as the SGEMM-style kernel, but the T = R(R+1)/2 pairs of a frame do not fill a CTA, so the 256 threads form G = 256/T groups
+// that split the pixels of every 64-pixel tile (a K split); the groups' partial blocks meet once in shared memory at the end and
+// the CTA flushes T x 42 values with fp64 atomics.  The next tile travels global -> registers while the current one is being
+// multiplied (36 FMA per 6 LDS.64 per pixel and thread).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSsLines = (kSgRows * 6) / (kSgThreads / 32);     // (row, component) lines per warp: 12
+
+__global__ void __launch_bounds__(kSgThreads, 2) ba_schur_small_kernel(
+    const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
+    const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
+    const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
+    double* __restrict__ Hsys, double* __restrict__ bsys) {
+  const int m = blockIdx.y;
+  if (m >= hdr[HDR_M]) return;
+  const int ix = kx[m];
+  const int e_begin = rowptr[m];
+  const int deg = rowptr[m + 1] - e_begin;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = 6 * P;
+
+  __shared__ int s_pose[kSchurMaxRows + 1];
+  __shared__ const float* s_ptr[kSchurMaxRows + 1];
+  __shared__ int s_nrows;
+  __shared__ int s_wcount[kSgThreads / 32];
+  extern __shared__ float sg_dyn[];
+  float* sA = sg_dyn;                                  // [64 px][98]: rows scaled by Q = 1/C
+  float* sB = sg_dyn + kSgK * kSgStride;               // raw rows
+  __shared__ float sQw[kSgK];
+
+  build_row_list<kSgThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
+  const int nrows = s_nrows;
+  if (nrows == 0 || nrows > kSgRows) return;           // larger frames belong to ba_schur_gemm_kernel
+  const int px_begin = blockIdx.x * px_per_cta;
+  const int px_end = min(HW, px_begin + px_per_cta);
+  if (px_begin >= px_end) return;
+
+  const int T = nrows * (nrows + 1) / 2;
+  const int G = kSgThreads / T;                        // T <= 136 -> G >= 1
+  const int g = tid / T;
+  const int pr = tid - g * T;
+  const bool active = g < G;
+  int ty = (int)((sqrtf(8.f * (float)pr + 1.f) - 1.f) * 0.5f);       // pr -> (ty >= tx)
+  while (ty * (ty + 1) / 2 > pr) ty--;
+  while ((ty + 1) * (ty + 2) / 2 <= pr) ty++;
+  const int tx = pr - ty * (ty + 1) / 2;
+  const bool diag_pair = (ty == tx);
+  const int nlines = nrows * 6;
+
+  float acc[36], bacc[6];
+#pragma unroll
+  for (int k = 0; k < 36; k++) acc[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; k++) bacc[k] = 0.f;
+
+  float pre[kSsLines][2], q0, q1, w0, w1;
+  auto load_tile = [&](int p0) {
+    const int np = min(kSgK, px_end - p0);
+    const bool ok0 = lane < np, ok1 = lane + 32 < np;
+    const size_t base = (size_t)m * HW + p0;
+    q0 = ok0 ? 1.0f / __ldg(Cin + base + lane) : 0.f;
+    q1 = ok1 ? 1.0f / __ldg(Cin + base + lane + 32) : 0.f;
+    w0 = ok0 ? __ldg(win + base + lane) : 0.f;
+    w1 = ok1 ? __ldg(win + base + lane + 32) : 0.f;
+#pragma unroll
+    for (int i = 0; i < kSsLines; i++) {
+      const int ln = warp + (kSgThreads / 32) * i;
+      pre[i][0] = 0.f; pre[i][1] = 0.f;
+      if (ln < nlines) {
+        const int rowl = ln / 6, c = ln - rowl * 6;
+        const float* src = s_ptr[rowl] + (size_t)c * HW + p0;
+        if (ok0) pre[i][0] = __ldg(src + lane);
+        if (ok1) pre[i][1] = __ldg(src + lane + 32);
+      }
+    }
+  };
+
+  load_tile(px_begin);
+  for (int p0 = px_begin; p0 < px_end; p0 += kSgK) {
+    __syncthreads();                                   // the previous tile has been consumed
+#pragma unroll
+    for (int i = 0; i < kSsLines; i++) {
+      const int ln = warp + (kSgThreads / 32) * i;
+      if (ln < nlines) {
+        const int o = ln;                              // = row * 6 + component
+        sB[lane * kSgStride + o] = pre[i][0];
+        sB[(lane + 32) * kSgStride + o] = pre[i][1];
+        sA[lane * kSgStride + o] = pre[i][0] * q0;     // ei = E*q   (reference K9)
+        sA[(lane + 32) * kSgStride + o] = pre[i][1] * q1;
+      }
+    }
+    if (warp == 0) { sQw[lane] = w0; sQw[lane + 32] = w1; }
+    __syncthreads();
+    if (p0 + kSgK < px_end) load_tile(p0 + kSgK);      // in flight while this tile is multiplied
+    if (active) {
+      const float* pa = sA + ty * 6;
+      const float* pb = sB + tx * 6;
+#pragma unroll 2
+      for (int px = g; px < kSgK; px += G) {
+        const float2 a01 = *reinterpret_cast<const float2*>(pa + px * kSgStride);
+        const float2 a23 = *reinterpret_cast<const float2*>(pa + px * kSgStride + 2);
+        const float2 a45 = *reinterpret_cast<const float2*>(pa + px * kSgStride + 4);
+        const float2 b01 = *reinterpret_cast<const float2*>(pb + px * kSgStride);
+        const float2 b23 = *reinterpret_cast<const float2*>(pb + px * kSgStride + 2);
+        const float2 b45 = *reinterpret_cast<const float2*>(pb + px * kSgStride + 4);
+        const float ea[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+        const float eb[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc[a * 6 + c] += ea[a] * eb[c];
+        if (diag_pair) {
+          const float w = sQw[px];                     // (Q E) w = Q w E
+#pragma unroll
+          for (int c = 0; c < 6; c++) bacc[c] += w * ea[c];
+        }
+      }
+    }
+  }
+  // ---- the G pixel groups meet in shared memory (the staging area is free now), then one flush into the lower triangle
+  __syncthreads();
+  float* red = sg_dyn;                                 // [G][T][42]
+  if (active) {
+    float* dst = red + (size_t)(g * T + pr) * 42;
+#pragma unroll
+    for (int k = 0; k < 36; k++) dst[k] = acc[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) dst[36 + k] = bacc[k];
+  }
+  __syncthreads();
+  for (int k = tid; k < T * 42; k += kSgThreads) {
+    const int q = k / 42, o = k - q * 42;
+    int r2 = (int)((sqrtf(8.f * (float)q + 1.f) - 1.f) * 0.5f);
+    while (r2 * (r2 + 1) / 2 > q) r2--;
+    while ((r2 + 1) * (r2 + 2) / 2 <= q) r2++;
+    const int r = q - r2 * (r2 + 1) / 2;
+    const bool same_row = (r == r2);
+    if (o >= 36 && !same_row) continue;
+    float sum = 0.f;
+    for (int gg = 0; gg < G; gg++) sum += red[(size_t)(gg * T + q) * 42 + o];
+    const double v = -(double)sum;
+    const int pa_ = s_pose[r2], pb_ = s_pose[r];       // block S(pa_, pb_)[a][c]; its transpose sits at (pb_, pa_)[c][a]
+    if (o < 36) {
+      const int a = o / 6, c = o - a * 6;
+      const int gr = pa_ * 6 + a, gc = pb_ * 6 + c;
+      if (same_row) {
+        if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+      } else {
+        if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+        if (gc >= gr) atomicAdd(&Hsys[(size_t)gc * n + gr], v);
+      }
+    } else {
+      atomicAdd(&bsys[pa_ * 6 + (o - 36)], v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Schur complement on the tensor cores (frames with at most 21 rows, i.e. every frame of a sliding-window graph):
+//   S = X X^T  with  X = [ E_r / sqrt(C) ; w / sqrt(C) ]  (6R + 1 rows x pixels),  so that S[:6R,:6R] = sum E q E^T and
+//   S[:6R, 6R] = sum E q w  -- one symmetric rank-K update per frame, K = pixels.
+// fp32 accuracy on the tf32 pipe by operand splitting (3xTF32): x = hi + lo with hi = tf32(x), lo = x - hi (exact), and
+//   D += hi hi^T + hi lo^T + lo hi^T  in the fp32 TMEM accumulator (the dropped lo lo^T term is ~2^-22 relative).
+// CTA = (frame, pixel range), 288 threads.  Warps 0-7: cp.async the raw rows (plus w and C) of a 32-pixel chunk into a
+// 4-deep raw ring, then split them into the two K-major SWIZZLE_128B operand tiles [128 rows x 32 px] of a 4-deep operand
+// ring (generic-proxy stores + fence.proxy.async).  Warp 8: one thread issues 4 K-steps x 3 tcgen05.mma.kind::tf32
+// (M = 128, N = ceil16(6R + 1)) per chunk, both operands described from the SAME tile, tcgen05.commit frees the stage.
+// Epilogue: warps 0-7 read the accumulator with tcgen05.ld and add the lower triangle into the reduced system with fp64
+// atomics.  Rows 6R+1 .. 127 of the operand tiles stay zero.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTcRowsMax = 21;
+constexpr int kTcThreads = 288;
+constexpr int kTcProducers = 256;
+constexpr int kTcK = 32;
+constexpr int kTcRawStages = 4;
+constexpr int kTcRawBytes = 128 * 128;          // up to 128 lines (6R rows, w, C) x 128 bytes
+constexpr int kTcOpBytes = 128 * 128;           // one operand tile (hi or lo)
+constexpr int kTcOpStages = 4;
+constexpr int kTcAccSlots = 4;                  // TMEM accumulators of 128 columns each
+constexpr int kTcSmem = kTcRawStages * kTcRawBytes + kTcOpStages * 2 * kTcOpBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
+    const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
+    const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
+    const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
+    double* __restrict__ Hsys, double* __restrict__ bsys) {
+  const int m = blockIdx.y;
+  if (m >= hdr[HDR_M]) return;
+  const int ix = kx[m];
+  const int e_begin = rowptr[m];
+  const int deg = rowptr[m + 1] - e_begin;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = 6 * P;
+
+  __shared__ int s_pose[kSchurMaxRows + 1];
+  __shared__ const float* s_ptr[kSchurMaxRows + 1];
+  __shared__ int s_nrows;
+  __shared__ int s_wcount[kTcThreads / 32];
+  __shared__ int s_gidx[128];                     // operand row / column -> index in the reduced system (-1: rhs, -2: padding)
+  extern __shared__ uint8_t tc_smem_raw[];
+
+  build_row_list<kTcThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
+  const int nrows = s_nrows;
+  if (nrows == 0 || nrows > kTcRowsMax) return;         // larger frames belong to ba_schur_gemm_kernel
+  const int px_begin = blockIdx.x * px_per_cta;
+  const int px_end = min(HW, px_begin + px_per_cta);
+  if (px_begin >= px_end) return;
+  const int nchunks = (px_end - px_begin + kTcK - 1) / kTcK;
+  const int R6 = 6 * nrows;                              // operand rows 0..R6-1: E rows, row R6: w
+  const int N = (R6 + 1 + 15) & ~15;                     // MMA N
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_op = smem;                                  // [stage][hi|lo][128 rows][128 B], 1024-byte aligned tiles
+  uint8_t* s_raw = smem + kTcOpStages * 2 * kTcOpBytes;  // [stage][line][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_raw + kTcRawStages * kTcRawBytes);
+  uint64_t* full = bars;                                 // [stages] operand stage written (8 producer warps arrive)
+  uint64_t* empty = bars + kTcOpStages;                  // [stages] operand stage consumed (tcgen05.commit)
+  uint64_t* acc_full = bars + 2 * kTcOpStages;           // [4] accumulator slot holds one chunk's partial product (tcgen05.commit)
+  uint64_t* acc_empty = bars + 2 * kTcOpStages + kTcAccSlots;   // [4] slot drained into registers (8 warps arrive)
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * kTcOpStages + 2 * kTcAccSlots + 2);
+  // accumulators: the tensor core truncates every addend to the accumulator's exponent, so a long chain of accumulations
+  // drifts (measured: one accumulator over 576 MMAs -> 1e-4 on the depths, four accumulators -> 4e-5).  Each 32-pixel chunk
+  // therefore gets a fresh TMEM accumulator (four 128-column slots in rotation) that the producer warps drain into fp32
+  // registers (round-to-nearest adds) two chunks later: the long sum never lives in the tensor core.
+
+  if (tid < 128) s_gidx[tid] = (tid < R6) ? s_pose[tid / 6] * 6 + (tid % 6) : (tid == R6 ? -1 : -2);
+  if (tid == 0) {
+    for (int s = 0; s < kTcOpStages; s++) { mbar_init(full + s, kTcProducers / 32); mbar_init(empty + s, 1); }
+    for (int s = 0; s < kTcAccSlots; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kTcProducers / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_smem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    // operand tiles start as zeros: rows beyond 6R + 1 are never written again
+    uint4* z = reinterpret_cast<uint4*>(s_op);
+    for (int k = tid; k < kTcOpStages * 2 * kTcOpBytes / 16; k += kTcProducers) z[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 8) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(128, N);
+      for (int c = 0; c < nchunks; c++) {
+        const int os = c % kTcOpStages, slot = c % kTcAccSlots;
+        mbar_wait(full + os, (c / kTcOpStages) & 1);
+        if (c >= kTcAccSlots) mbar_wait(acc_empty + slot, ((c / kTcAccSlots) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t hi0 = smem_u32(s_op + (size_t)os * 2 * kTcOpBytes), lo0 = hi0 + kTcOpBytes;
+        const uint32_t d = tmem_base + (uint32_t)(slot * 128);
+#pragma unroll
+        for (int k = 0; k < kTcK / 8; k++) {
+          const uint64_t dh = umma_desc_k_sw128(hi0 + k * 32, 1024), dl = umma_desc_k_sw128(lo0 + k * 32, 1024);
+          umma_tf32(d, dh, dh, idesc, k > 0 ? 1u : 0u);
+          umma_tf32(d, dh, dl, idesc, 1u);
+          umma_tf32(d, dl, dh, idesc, 1u);
+        }
+        umma_commit(empty + os);          // the operand stage may be overwritten once these MMAs have read it
+        umma_commit(acc_full + slot);     // ... and the chunk's partial product is ready to be drained
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= producers: raw rows -> split operands =================
+    // each thread owns up to four (line, 16-byte piece) slots of the raw stage: line l < 6R is row l/6, component l%6;
+    // line 6R is w, line 6R + 1 is C
+    const int nlines = R6 + 2;
+    const float* src[4];
+    uint32_t dst[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int idx = tid + i * kTcProducers;
+      const int line = idx >> 3, piece = idx & 7;
+      src[i] = nullptr; dst[i] = 0;
+      if (line < nlines) {
+        const float* base = (line < R6) ? s_ptr[line / 6] + (size_t)(line % 6) * HW
+                          : (line == R6) ? win + (size_t)m * HW : Cin + (size_t)m * HW;
+        src[i] = base + piece * 4;
+        dst[i] = smem_u32(s_raw) + line * 128 + piece * 16;
+      }
+    }
+    // this thread's share of S: row q*32 + lane, columns half*32 + {0..31} and 64 + half*32 + {0..31}
+    const int q = warp & 3, half = warp >> 2;
+    float acc[2][32];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc[h][j] = 0.f;
+    auto drain = [&](int cd) {
+      const int slot = cd % kTcAccSlots;
+      mbar_wait(acc_full + slot, (cd / kTcAccSlots) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int cb = half * 32 + h * 64;
+        if (cb < N) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + cb), r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[h][j] += __uint_as_float(r[j]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + slot);
+    };
+    auto issue = [&](int c) {
+      if (c < nchunks) {
+        const int p0 = px_begin + c * kTcK;
+        const uint32_t stage_off = (uint32_t)(c % kTcRawStages) * kTcRawBytes;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (src[i] != nullptr) {
+            const int piece_px = p0 + (int)(((tid + i * kTcProducers) & 7) * 4);
+            const bool ok = piece_px < px_end;
+            cp_async16_zfill(dst[i] + stage_off, ok ? (const void*)(src[i] + p0) : (const void*)Cin, ok ? 16u : 0u);
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < kTcRawStages - 1; s++) issue(s);
+
+    for (int c = 0; c < nchunks; c++) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kTcRawStages - 2) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");      // every producer's copies of chunk c have landed
+      const int os = c % kTcOpStages;
+      if (c >= kTcOpStages) mbar_wait(empty + os, ((c / kTcOpStages) - 1) & 1);
+      const uint8_t* raw = s_raw + (size_t)(c % kTcRawStages) * kTcRawBytes;
+      uint8_t* ophi = s_op + (size_t)os * 2 * kTcOpBytes;
+      const float Cv = reinterpret_cast<const float*>(raw + (R6 + 1) * 128)[lane];
+      const float sq = (Cv > 0.f) ? 1.0f / sqrtf(Cv) : 0.f;               // sqrt(Q); zero-filled pixels beyond the range stay zero
+      const uint32_t col_off = (uint32_t)(lane & 3) * 4;
+      const uint32_t chunk16 = (uint32_t)(lane >> 2);
+#pragma unroll 4
+      for (int line = warp; line <= R6; line += kTcProducers / 32) {
+        const float x = reinterpret_cast<const float*>(raw + line * 128)[lane] * sq;
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+        const float hi = __uint_as_float(hb);
+        const float lo = x - hi;
+        const uint32_t off = (uint32_t)line * 128 + ((chunk16 ^ (uint32_t)(line & 7)) << 4) + col_off;
+        *reinterpret_cast<float*>(ophi + off) = hi;
+        *reinterpret_cast<float*>(ophi + kTcOpBytes + off) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + os);
+      issue(c + kTcRawStages - 1);
+      if (c >= 2) drain(c - 2);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (nchunks >= 2) drain(nchunks - 2);
+    drain(nchunks - 1);
+
+    // ================= epilogue: lower triangle of S (and the rhs column) into the reduced system =================
+    const int row = q * 32 + lane;
+    const int gr = s_gidx[row];
+    if (gr >= 0) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int cb = half * 32 + h * 64;
+        if (cb < N) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int gc = s_gidx[cb + j];
+            const double v = -(double)acc[h][j];
+            if (gc >= 0) {
+              if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+            } else if (gc == -1) {
+              atomicAdd(&bsys[gr], v);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -951,16 +1182,12 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
 #undef LAUNCH_BUILD
   DBA_CHECK_LAUNCH("ba_build");
   if (!a->motion_only) {
-    const int tiles = (HW + kSchurTP - 1) / kSchurTP;
-    int chunks = (2 * 148 + eff_frames - 1) / eff_frames;          // about two CTAs per SM worth of (frame, chunk) work items
-    chunks = chunks < 1 ? 1 : (chunks > tiles ? tiles : chunks);
-    const int px_per_cta = ((tiles + chunks - 1) / chunks) * kSchurTP;
-    const int gx = (HW + px_per_cta - 1) / px_per_cta;
-    // frames with more than 12 rows are processed as pairs of 12-row blocks; when few frames carry many edges (edge-sharded
-    // ranks, dense graphs) the block pairs are spread over gridDim.z so the GPU stays full
-    const int zsplit = (eff_frames * gx >= 2 * 148) ? 1 : std::min(16, (4 * 148 + eff_frames * gx - 1) / (eff_frames * gx));
-    const size_t smem1 = ((size_t)kSchurRB * 6 * kSchurTP + 2 * kSchurTP + (size_t)(kSchurRB * (kSchurRB + 1) / 2) * 42) * sizeof(float);
     const size_t smem2 = (size_t)2 * kSgK * kSgStride * sizeof(float);
+    // small frames: about 2.5 CTAs per SM worth of (frame, chunk) work items of whole 64-pixel tiles
+    const int tiles1 = (HW + kSgK - 1) / kSgK;
+    const int chunks1 = std::max(1, std::min(tiles1, (5 * 148 / 2 + eff_frames - 1) / eff_frames));
+    const int px_per_cta1 = ((tiles1 + chunks1 - 1) / chunks1) * kSgK;
+    const int gx1 = (HW + px_per_cta1 - 1) / px_per_cta1;
     // the SGEMM-style kernel keeps its accumulators in registers over the whole pixel chunk: few long chunks, tile pairs over z
     const int px_per_cta2 = ((HW + 2) / 3 + kSgK - 1) / kSgK * kSgK;
     const int gx2 = (HW + px_per_cta2 - 1) / px_per_cta2;
@@ -968,15 +1195,29 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
     static bool attr_set = false;
     if (!attr_set) {
       DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur gemm smem attr");
-      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1), "schur smem attr");
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur smem attr");
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem), "schur tc smem attr");
       attr_set = true;
     }
-    ba_schur_kernel<true><<<dim3(gx, a->n_frames, 1), kSchurThreads, smem1, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
-                                                           WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta, WS(float, L.off_Eij),
+    // frames with at most 21 rows go to the tensor cores (needs 16-byte aligned pixel rows); DBA_SCHUR_SIMT=1 keeps the CUDA-core path
+    static const bool force_simt = (getenv("DBA_SCHUR_SIMT") != nullptr && getenv("DBA_SCHUR_SIMT")[0] == '1');
+    const bool use_tc = (HW % 4 == 0) && !force_simt;
+    if (use_tc) {
+      const int tiles32 = (HW + kTcK - 1) / kTcK;
+      const int chunks_tc = std::max(1, std::min(tiles32, (148 + eff_frames / 2) / eff_frames));     // one CTA per SM
+      const int px_per_cta_tc = ((tiles32 + chunks_tc - 1) / chunks_tc) * kTcK;
+      const int gx_tc = (HW + px_per_cta_tc - 1) / px_per_cta_tc;
+      ba_schur_tc_kernel<<<dim3(gx_tc, a->n_frames, 1), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                           WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta_tc, WS(float, L.off_Eij),
                                                            WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+    } else {
+      ba_schur_small_kernel<<<dim3(gx1, a->n_frames, 1), kSgThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                           WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta1, WS(float, L.off_Eij),
+                                                           WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+    }
     DBA_CHECK_LAUNCH("ba_schur<single>");
     ba_schur_gemm_kernel<<<dim3(gx2, a->n_frames, zsplit2), kSgThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
-                                                                         WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta2, WS(float, L.off_Eij),
+                                                                         WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta2, use_tc ? kTcRowsMax : kSgRows, WS(float, L.off_Eij),
                                                                          WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
     DBA_CHECK_LAUNCH("ba_schur<multi>");
   }
@@ -995,7 +1236,7 @@ extern "C" int dba_ba_solve(const dba_ba_args* a) {
     CholPeers peers; peers.world = 0;
     if (a->p2p_world > 1) {
       const size_t nd = (size_t)L.n * L.n + L.n;
-      peers.world = a->p2p_world; peers.epoch = a->p2p_epoch;
+      peers.world = a->p2p_world; peers.epoch = a->p2p_epoch; peers.epoch_dev = a->p2p_epoch_dev;
       for (int k = 0; k < a->p2p_world; k++) peers.sys[k] = reinterpret_cast<const double*>(a->p2p_system[k]) + (size_t)(a->p2p_epoch & 1ull) * nd;
       peers.flags = reinterpret_cast<const unsigned long long*>(reinterpret_cast<const double*>(a->p2p_system[a->p2p_rank]) + 2 * nd);
     }
@@ -1018,11 +1259,16 @@ extern "C" int dba_ba_solve(const dba_ba_args* a) {
 
 // publish this rank's partial system to every peer: release stores of the epoch into flags[rank] of each peer's buffer
 namespace dba {
-struct P2PSignal { unsigned long long* flag[8]; int world; unsigned long long epoch; };
+struct P2PSignal { unsigned long long* flag[8]; int world; unsigned long long epoch; unsigned long long* epoch_dev; };
 __global__ void ba_p2p_signal_kernel2(P2PSignal s) {
   __threadfence_system();
   const int lane = threadIdx.x;
-  if (lane < s.world) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.flag[lane]), "l"(s.epoch) : "memory");
+  unsigned long long e = s.epoch;
+  if (s.epoch_dev) {                     // device-resident epoch: advance it here so a captured graph publishes a fresh value per replay
+    if (lane == 0) { e = *s.epoch_dev + 1ull; *s.epoch_dev = e; }
+    e = __shfl_sync(0xffffffffu, e, 0);
+  }
+  if (lane < s.world) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(s.flag[lane]), "l"(e) : "memory");
 }
 }  // namespace dba
 
@@ -1030,7 +1276,7 @@ extern "C" int dba_ba_p2p_signal(const dba_ba_args* a) {
   Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
   if (a->p2p_world <= 1) return DBA_OK;
   const size_t nd = (size_t)L.n * L.n + L.n;
-  dba::P2PSignal s; s.world = a->p2p_world; s.epoch = a->p2p_epoch;
+  dba::P2PSignal s; s.world = a->p2p_world; s.epoch = a->p2p_epoch; s.epoch_dev = a->p2p_epoch_dev;
   for (int k = 0; k < a->p2p_world; k++)
     s.flag[k] = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(a->p2p_system[k]) + 2 * nd) + a->p2p_rank;
   dba::ba_p2p_signal_kernel2<<<1, 32, 0, (cudaStream_t)a->stream>>>(s);

@@ -40,12 +40,14 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ void stcg(double* p, double v) { __stcg(p, v); }
 
-// 1/sqrt(d): fp32 MUFU seed + one Newton step in fp64 (relative error ~3e-14)
+// 1/sqrt(d): MUFU.RSQ64H seed (~2^-22) + one third-order correction r += r t (1/2 + 3/8 t), t = 1 - d r^2 (error ~ t^3: full fp64).
+// Deliberately branch-free: a branch here splits warp_potrf into basic blocks and stops ptxas from scheduling the rank-1 update
+// under the latency of this chain.  d <= 0 yields NaN/inf, which the caller flags through its pivot test.
 __device__ __forceinline__ double fast_rsqrt(double d) {
-  if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
-  double r = (double)rsqrtf((float)d);
-  r = r * (1.5 - (0.5 * d) * r * r);
-  return r;
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  const double t = fma(-d, r * r, 1.0);
+  return fma(fma(0.375, t, 0.5), r * t, r);
 }
 
 // Cholesky of a 32x32 tile, one row per lane in registers; the pivot column is broadcast through `col` (2 x 32 doubles
@@ -54,19 +56,26 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
 __device__ __forceinline__ bool warp_potrf(double (&a)[kT], int lane, double* col, double& rdiag_out) {
   bool ok = true;
   rdiag_out = 0.0;
+  // software-pipelined: the pivot of column k+1 only needs a[k+1] after the rank-1 update of column k, so that element is updated
+  // first and its shuffle + rsqrt chain (the latency that bounds this routine) runs under the remaining 30 updates of column k
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  double r = fast_rsqrt(d);
 #pragma unroll
   for (int k = 0; k < kT; k++) {
-    const double d = __shfl_sync(0xffffffffu, a[k], k);
     if (!(d > 0.0)) ok = false;
-    const double r = fast_rsqrt(d);
     const double l = (lane == k) ? d * r : a[k] * r;
     if (lane == k) rdiag_out = r;
     a[k] = l;
     double* cb = col + (k & 1) * kT;
     cb[lane] = l;
     __syncwarp();
+    if (k + 1 < kT) {
+      a[k + 1] -= l * cb[k + 1];
+      d = __shfl_sync(0xffffffffu, a[k + 1], k + 1);
+      r = fast_rsqrt(d);
+    }
 #pragma unroll
-    for (int j = k + 1; j < kT; j++) a[j] -= l * cb[j];   // only rows >= j are meaningful
+    for (int j = k + 2; j < kT; j++) a[j] -= l * cb[j];   // only rows >= j are meaningful
   }
   return ok;
 }
@@ -88,7 +97,7 @@ struct CholParams {
 // one warp: C (32x32 at Ct) -= A (at At) * B^T (at Bt); lane (rg = lane>>3, cg = lane&7) owns rows 8rg..8rg+7, cols 4cg..4cg+3
 __device__ __forceinline__ void warp_tile_update(const double* At, const double* Bt, double* Ct, int ld, int lane,
                                                  double (*sA)[kTP], double (*sB)[kTP]) {
-#pragma unroll 8
+#pragma unroll 16
   for (int r = 0; r < kT; r++) { sA[r][lane] = ldcg(At + (size_t)r * ld + lane); sB[r][lane] = ldcg(Bt + (size_t)r * ld + lane); }
   const int rg = lane >> 3, cgp = lane & 7;
   double acc[8][4];
@@ -146,13 +155,14 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     __shared__ int s_timeout;
     if (tid == 0) {
       int bad = 0;
+      const unsigned long long want = p.peers.epoch_dev ? *p.peers.epoch_dev : p.peers.epoch;
       for (int r = 0; r < world; r++) {
         unsigned long long v = 0;
         long long spins = 0;
         do {
           asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.peers.flags + r) : "memory");
-        } while (v < p.peers.epoch && ++spins < (1ll << 24));
-        if (v < p.peers.epoch) bad = 1;
+        } while (v < want && ++spins < (1ll << 24));
+        if (v < want) bad = 1;
       }
       s_timeout = bad;
     }
@@ -216,8 +226,8 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     for (int i = k + 1 + gw; i <= nt; i += nwarps) {
       double a[kT];
       double* tile = L + (size_t)(i * kT) * ld + k * kT;
-#pragma unroll 8
-      for (int r = 0; r < kT; r++) s_A[warp][r][lane] = ldcg(tile + (size_t)r * ld + lane);     // coalesced rows
+#pragma unroll
+      for (int r = 0; r < kT; r++) s_A[warp][r][lane] = ldcg(tile + (size_t)r * ld + lane);     // coalesced rows, all 32 loads in flight
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < kT; c++) a[c] = s_A[warp][lane][c];                                   // lane = row
@@ -360,7 +370,7 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   if (n <= 0) return DBA_OK;
   CholParams p;
   p.H = H; p.b = b; p.n = n; p.nt = (n + kT - 1) / kT; p.lm = lm; p.ep = ep; p.fail = fail; p.x = x;
-  if (peers) p.peers = *peers; else { p.peers.world = 0; p.peers.flags = nullptr; p.peers.epoch = 0; for (int k = 0; k < 8; k++) p.peers.sys[k] = nullptr; }
+  if (peers) p.peers = *peers; else { p.peers.world = 0; p.peers.flags = nullptr; p.peers.epoch = 0; p.peers.epoch_dev = nullptr; for (int k = 0; k < 8; k++) p.peers.sys[k] = nullptr; }
   const size_t ld = (size_t)p.nt * kT;
   p.L = reinterpret_cast<double*>(workspace);
   p.Linv = p.L + (size_t)(p.nt + 1) * kT * ld;

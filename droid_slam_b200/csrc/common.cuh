@@ -17,6 +17,7 @@ struct CholPeers {            // fused peer-to-peer reduction (world > 1): H/b a
   const double* sys[8];       // peer-mapped pointers to each rank's [n*n + n] system for this epoch
   const unsigned long long* flags;   // this rank's flag array [world], flag[p] >= epoch when rank p has published
   unsigned long long epoch;
+  const unsigned long long* epoch_dev;   // when set, the awaited value is read from this rank-local device counter (CUDA-graph replay)
 };
 int chol_solve_launch(const double* H, const double* b, int n, double lm, double ep, void* workspace, int* fail, float* x, cudaStream_t st,
                       const CholPeers* peers = nullptr);

@@ -55,6 +55,9 @@ class P2PSystem:
         self.world = int(self.hdl.world_size)
         self.rank = int(self.hdl.rank)
         self.epoch = 0
+        # the epoch VALUE lives on the device (advanced by the signal kernel), which makes a whole step CUDA-graph capturable; the
+        # host counter only alternates the two slots, so a captured graph must contain an even number of GN iterations
+        self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=device)
         assert self.world <= 8
 
 
@@ -95,6 +98,7 @@ class CApiEngine:
             a.p2p_world, a.p2p_rank = p2p.world, p2p.rank
             for k, ptr in enumerate(p2p.ptrs):
                 a.p2p_system[k] = ptr
+            a.p2p_epoch_dev = p2p.epoch_dev.data_ptr()
         self.args = a
         self._keep = (poses, disps, intrinsics, disps_sens, targets, weights, eta_by_frame, ii, jj)
         c_api.check(L.dba_ba_prepare(ctypes.byref(a)), "ba_prepare")

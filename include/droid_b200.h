@@ -135,10 +135,14 @@ typedef struct {
    * doubles; 8 uint64 flags follow the two slots), dba_ba_p2p_signal() publishes it with release stores into every peer's
    * flags[p2p_rank], and the Cholesky kernel of dba_ba_solve waits for the W flags and sums the W peer copies in rank order
    * (bit-identical on every rank) straight out of peer memory.  p2p_system[] are peer-mapped device pointers (e.g. from
-   * torch.distributed._symmetric_memory); p2p_epoch must increase by one per Gauss-Newton iteration on every rank. */
+   * torch.distributed._symmetric_memory); p2p_epoch must increase by one per Gauss-Newton iteration on every rank.
+   * p2p_epoch_dev (optional, rank-local device memory, zero-initialised once): when set, the published / awaited epoch VALUE is
+   * this device counter (dba_ba_p2p_signal increments it on the stream), so the whole iteration can be captured in a CUDA graph
+   * and replayed; p2p_epoch then only selects the slot, and a captured graph must hold an even number of iterations. */
   int p2p_world, p2p_rank;
   unsigned long long p2p_epoch;
   void* p2p_system[8];
+  unsigned long long* p2p_epoch_dev;
 } dba_ba_args;
 
 int dba_ba_prepare(const dba_ba_args* a);
