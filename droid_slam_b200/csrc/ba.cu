@@ -772,28 +772,50 @@ __global__ void __launch_bounds__(kSgThreads, 2) ba_schur_small_kernel(
 //   S = X X^T  with  X = [ E_r / sqrt(C) ; w / sqrt(C) ]  (6R + 1 rows x pixels),  so that S[:6R,:6R] = sum E q E^T and
 //   S[:6R, 6R] = sum E q w  -- one symmetric rank-K update per frame, K = pixels.
 // fp32 accuracy on the tf32 pipe by operand splitting (3xTF32): x = hi + lo with hi = tf32(x), lo = x - hi (exact), and
-//   D += hi hi^T + hi lo^T + lo hi^T  in the fp32 TMEM accumulator (the dropped lo lo^T term is ~2^-22 relative).
-// CTA = (frame, pixel range), 288 threads.  Warps 0-7: cp.async the raw rows (plus w and C) of a 32-pixel chunk into a
-// 4-deep raw ring, then split them into the two K-major SWIZZLE_128B operand tiles [128 rows x 32 px] of a 4-deep operand
-// ring (generic-proxy stores + fence.proxy.async).  Warp 8: one thread issues 4 K-steps x 3 tcgen05.mma.kind::tf32
-// (M = 128, N = ceil16(6R + 1)) per chunk, both operands described from the SAME tile, tcgen05.commit frees the stage.
-// Epilogue: warps 0-7 read the accumulator with tcgen05.ld and add the lower triangle into the reduced system with fp64
-// atomics.  Rows 6R+1 .. 127 of the operand tiles stay zero.
+//   S = hi hi^T + G + G^T,  G = hi lo^T   (the dropped lo lo^T term is ~2^-22 relative),
+// i.e. TWO tcgen05.mma per 8-pixel K step: G is accumulated once and symmetrised in the epilogue.
+// The tensor core truncates every addend to the accumulator's exponent, so a long accumulation chain drifts (measured: one
+// accumulator over the whole pixel range -> 1e-4 on the depths).  hi hi^T therefore gets a fresh TMEM accumulator per chunk
+// (three 128-column slots in rotation) which the producer warps drain into fp32 registers two chunks later; G is 2^-11 smaller
+// and keeps one accumulator for the whole range.
+// CTA = (frame, pixel range), 288 threads.  Warps 0-7: cp.async their own raw rows of a chunk into a 4-deep warp-private raw ring,
+// split them into the two K-major SWIZZLE_128B operand tiles [128 rows x 32 px] of a 4-deep operand ring (generic-proxy stores +
+// fence.proxy.async), drain accumulators, and finally add the lower triangle into the reduced system with fp64 atomics.
+// Warp 8: one thread issues the MMAs (M = 128, both operands described from the SAME tile) and commits to the mbarriers.
+// Frames with 6R + 2 <= 64 (R <= 10) run "packed": the two halves of a 64-pixel chunk sit in operand rows 0..63 and 64..127,
+// one M = N = 128 MMA then yields both halves' products on the diagonal blocks (the MMA cost is set by the 128 operand rows
+// it streams whether they are live or not), and the epilogue adds the two blocks.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTcRowsMax = 21;
 constexpr int kTcThreads = 288;
 constexpr int kTcProducers = 256;
-constexpr int kTcK = 32;
 constexpr int kTcRawStages = 4;
-constexpr int kTcRawBytes = 128 * 128;          // up to 128 lines (6R rows, w, C) x 128 bytes
+constexpr int kTcRawBytes = 128 * 128;          // up to 128 lines (6R rows, w, C; two halves when packed) x 128 bytes
 constexpr int kTcOpBytes = 128 * 128;           // one operand tile (hi or lo)
 constexpr int kTcOpStages = 4;
-constexpr int kTcAccSlots = 4;                  // TMEM accumulators of 128 columns each
+constexpr int kTcAccSlots = 3;                  // rotating TMEM accumulators (128 columns each) for hi hi^T; G lives in columns 384..511
+constexpr int kTcCxStride = 129;                // floats per row of the G staging matrix (conflict-free transposed reads)
 constexpr int kTcSmem = kTcRawStages * kTcRawBytes + kTcOpStages * 2 * kTcOpBytes + 1024 /*alignment*/ + 256 /*barriers*/;
+static_assert(128 * kTcCxStride * 4 <= kTcOpStages * 2 * kTcOpBytes, "G staging matrix must fit the operand ring");
 
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+
+// debug timeline (DBA_TC_TIMING build only): globaltimer stamps of one CTA's warp 0 / MMA thread
+#ifdef DBA_TC_TIMING
+__device__ unsigned long long g_tc_timing[8192];
+__device__ __forceinline__ unsigned long long tc_gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TC_STAMP(cond, idx) do { if (cond) g_tc_timing[(idx)] = tc_gtimer(); } while (0)
+#else
+#define TC_STAMP(cond, idx) do {} while (0)
+#endif
 
 __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
     const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
@@ -821,87 +843,108 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
   const int px_begin = blockIdx.x * px_per_cta;
   const int px_end = min(HW, px_begin + px_per_cta);
   if (px_begin >= px_end) return;
-  const int nchunks = (px_end - px_begin + kTcK - 1) / kTcK;
   const int R6 = 6 * nrows;                              // operand rows 0..R6-1: E rows, row R6: w
-  const int N = (R6 + 1 + 15) & ~15;                     // MMA N
+  TC_STAMP(blockIdx.x == 0 && blockIdx.y == 20 && threadIdx.x == 0, 7);
+  const bool packed = (R6 + 2 <= 64);
+  const int nhalf = packed ? 2 : 1;
+  const int cpx = 32 * nhalf;                            // pixels per chunk
+  const int nchunks = (px_end - px_begin + cpx - 1) / cpx;
+  const int N = packed ? 128 : ((R6 + 1 + 15) & ~15);    // MMA N
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* s_op = smem;                                  // [stage][hi|lo][128 rows][128 B], 1024-byte aligned tiles
-  uint8_t* s_raw = smem + kTcOpStages * 2 * kTcOpBytes;  // [stage][line][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_raw + kTcRawStages * kTcRawBytes);
-  uint64_t* full = bars;                                 // [stages] operand stage written (8 producer warps arrive)
-  uint64_t* empty = bars + kTcOpStages;                  // [stages] operand stage consumed (tcgen05.commit)
-  uint64_t* acc_full = bars + 2 * kTcOpStages;           // [4] accumulator slot holds one chunk's partial product (tcgen05.commit)
-  uint64_t* acc_empty = bars + 2 * kTcOpStages + kTcAccSlots;   // [4] slot drained into registers (8 warps arrive)
-  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(bars + 2 * kTcOpStages + 2 * kTcAccSlots + 2);
-  // accumulators: the tensor core truncates every addend to the accumulator's exponent, so a long chain of accumulations
-  // drifts (measured: one accumulator over 576 MMAs -> 1e-4 on the depths, four accumulators -> 4e-5).  Each 32-pixel chunk
-  // therefore gets a fresh TMEM accumulator (four 128-column slots in rotation) that the producer warps drain into fp32
-  // registers (round-to-nearest adds) two chunks later: the long sum never lives in the tensor core.
+  const uint32_t op_base = smem_u32(smem);               // [stage][hi|lo][128 rows][128 B], 1024-byte aligned tiles
+  const uint32_t raw_base = op_base + kTcOpStages * 2 * kTcOpBytes;   // [stage][row][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcOpStages * 2 * kTcOpBytes + kTcRawStages * kTcRawBytes);
+  uint64_t* full = bars;                                 // [4] operand stage written (8 producer warps arrive)
+  uint64_t* empty = bars + kTcOpStages;                  // [4] operand stage consumed (tcgen05.commit)
+  uint64_t* acc_full = bars + 2 * kTcOpStages;           // [3] accumulator slot holds one chunk's hi hi^T (tcgen05.commit)
+  uint64_t* acc_empty = acc_full + kTcAccSlots;          // [3] slot drained into registers (8 warps arrive)
+  uint64_t* done = acc_empty + kTcAccSlots;              // every MMA has completed
+  uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(done + 2);
 
   if (tid < 128) s_gidx[tid] = (tid < R6) ? s_pose[tid / 6] * 6 + (tid % 6) : (tid == R6 ? -1 : -2);
   if (tid == 0) {
     for (int s = 0; s < kTcOpStages; s++) { mbar_init(full + s, kTcProducers / 32); mbar_init(empty + s, 1); }
     for (int s = 0; s < kTcAccSlots; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kTcProducers / 32); }
+    mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_base_smem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   } else {
-    // operand tiles start as zeros: rows beyond 6R + 1 are never written again
-    uint4* z = reinterpret_cast<uint4*>(s_op);
+    // operand tiles start as zeros: rows that carry no line are never written again
+    uint4* z = reinterpret_cast<uint4*>(smem);
     for (int k = tid; k < kTcOpStages * 2 * kTcOpBytes / 16; k += kTcProducers) z[k] = make_uint4(0u, 0u, 0u, 0u);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_base_smem;
+  const bool dbg = (blockIdx.x == 0 && blockIdx.y == 20);
+  const bool dbg0 = dbg && tid == 0;
+  TC_STAMP(dbg0, 0);
+#ifdef DBA_TC_TIMING
+  if (dbg0) { g_tc_timing[1] = (unsigned long long)nchunks; g_tc_timing[2] = (unsigned long long)R6; }
+#endif
 
   if (warp == 8) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(128, N);
+      const uint32_t d_g = tmem_base + 3 * 128;
       for (int c = 0; c < nchunks; c++) {
         const int os = c % kTcOpStages, slot = c % kTcAccSlots;
+        TC_STAMP(dbg, 4096 + 4 * c + 0);
         mbar_wait(full + os, (c / kTcOpStages) & 1);
+        TC_STAMP(dbg, 4096 + 4 * c + 1);
         if (c >= kTcAccSlots) mbar_wait(acc_empty + slot, ((c / kTcAccSlots) - 1) & 1);
+        TC_STAMP(dbg, 4096 + 4 * c + 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t hi0 = smem_u32(s_op + (size_t)os * 2 * kTcOpBytes), lo0 = hi0 + kTcOpBytes;
+        const uint32_t hi0 = op_base + (uint32_t)os * 2 * kTcOpBytes, lo0 = hi0 + kTcOpBytes;
         const uint32_t d = tmem_base + (uint32_t)(slot * 128);
 #pragma unroll
-        for (int k = 0; k < kTcK / 8; k++) {
+        for (int k = 0; k < 4; k++) {
           const uint64_t dh = umma_desc_k_sw128(hi0 + k * 32, 1024), dl = umma_desc_k_sw128(lo0 + k * 32, 1024);
           umma_tf32(d, dh, dh, idesc, k > 0 ? 1u : 0u);
-          umma_tf32(d, dh, dl, idesc, 1u);
-          umma_tf32(d, dl, dh, idesc, 1u);
+          umma_tf32(d_g, dh, dl, idesc, (c > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty + os);          // the operand stage may be overwritten once these MMAs have read it
-        umma_commit(acc_full + slot);     // ... and the chunk's partial product is ready to be drained
+        umma_commit(acc_full + slot);     // ... and the chunk's hi hi^T is ready to be drained
+        TC_STAMP(dbg, 4096 + 4 * c + 3);
       }
+      umma_commit(done);
     }
     __syncwarp();
   } else {
     // ================= producers: raw rows -> split operands =================
-    // each thread owns up to four (line, 16-byte piece) slots of the raw stage: line l < 6R is row l/6, component l%6;
-    // line 6R is w, line 6R + 1 is C
-    const int nlines = R6 + 2;
+    // Every warp stages and splits its OWN lines (line = warp + 8 i), so the only CTA-wide coupling is through the mbarriers.
+    // Warp-private raw slab: 16 rows x 128 B per stage; slab row li = i (not packed) or hf * 8 + i (packed: half hf of the chunk).
+    // A thread owns four (slab row, 16-byte piece) copy slots: li = 4 s + lane / 8, piece = lane % 8.
     const float* src[4];
     uint32_t dst[4];
+    int pxo[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const int idx = tid + i * kTcProducers;
-      const int line = idx >> 3, piece = idx & 7;
-      src[i] = nullptr; dst[i] = 0;
-      if (line < nlines) {
-        const float* base = (line < R6) ? s_ptr[line / 6] + (size_t)(line % 6) * HW
-                          : (line == R6) ? win + (size_t)m * HW : Cin + (size_t)m * HW;
-        src[i] = base + piece * 4;
-        dst[i] = smem_u32(s_raw) + line * 128 + piece * 16;
+      const int li = 4 * i + (lane >> 3), piece = lane & 7;
+      const int hf = packed ? (li >> 3) : 0, line = warp + 8 * (packed ? (li & 7) : li);
+      src[i] = nullptr; dst[i] = 0; pxo[i] = 0;
+      if (line <= R6) {
+        const float* base = (line < R6) ? s_ptr[line / 6] + (size_t)(line % 6) * HW : win + (size_t)m * HW;
+        pxo[i] = hf * 32 + piece * 4;
+        src[i] = base + pxo[i];
+        dst[i] = raw_base + warp * 2048 + li * 128 + piece * 16;
       }
     }
-    // this thread's share of S: row q*32 + lane, columns half*32 + {0..31} and 64 + half*32 + {0..31}
-    const int q = warp & 3, half = warp >> 2;
+    const float* Cm = Cin + (size_t)m * HW;
+    // this thread's share of S: operand row q*32 + lane; column blocks of 32: packed -> the one block of its own half,
+    // otherwise half_w*32 and 64 + half_w*32
+    const int q = warp & 3, half_w = warp >> 2;
+    const int row = q * 32 + lane;
+    const int lrow = packed ? (row & 63) : row;                     // line of this row
+    const int lq = packed ? (q & 1) : q;                            // 32-row group inside the half
+    const int ncb = packed ? 1 : 2;
+    const int cb0 = packed ? ((q >> 1) * 64 + half_w * 32) : half_w * 32;
     float acc[2][32];
 #pragma unroll
     for (int h = 0; h < 2; h++)
@@ -913,8 +956,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int cb = half * 32 + h * 64;
-        if (cb < N) {
+        const int cb = cb0 + h * 64;
+        if (h < ncb && cb < N && lq * 32 < R6) {                     // warp-uniform: groups without live rows skip the TMEM read
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + cb), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -928,13 +971,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
     };
     auto issue = [&](int c) {
       if (c < nchunks) {
-        const int p0 = px_begin + c * kTcK;
+        const int p0 = px_begin + c * cpx;
         const uint32_t stage_off = (uint32_t)(c % kTcRawStages) * kTcRawBytes;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           if (src[i] != nullptr) {
-            const int piece_px = p0 + (int)(((tid + i * kTcProducers) & 7) * 4);
-            const bool ok = piece_px < px_end;
+            const bool ok = p0 + pxo[i] < px_end;
             cp_async16_zfill(dst[i] + stage_off, ok ? (const void*)(src[i] + p0) : (const void*)Cin, ok ? 16u : 0u);
           }
         }
@@ -944,53 +986,94 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
 #pragma unroll
     for (int s = 0; s < kTcRawStages - 1; s++) issue(s);
 
+    const uint32_t sw_col = (uint32_t)(lane & 3) * 4, sw_chunk = (uint32_t)(lane >> 2);
+    auto load_c = [&](int c, int hf) -> float {            // C of this lane's pixel in half hf of chunk c (0 beyond the range)
+      const int px = px_begin + c * cpx + hf * 32 + lane;
+      return (c < nchunks && px < px_end) ? __ldg(Cm + px) : 0.f;
+    };
+    float Cn0 = load_c(0, 0), Cn1 = packed ? load_c(0, 1) : 0.f;
+    TC_STAMP(dbg0, 3);
     for (int c = 0; c < nchunks; c++) {
+      TC_STAMP(dbg0, 16 + 8 * c + 0);
       asm volatile("cp.async.wait_group %0;" ::"n"(kTcRawStages - 2) : "memory");
-      asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");      // every producer's copies of chunk c have landed
+      __syncwarp();                                          // this warp's copies of chunk c have landed
+      TC_STAMP(dbg0, 16 + 8 * c + 1);
       const int os = c % kTcOpStages;
       if (c >= kTcOpStages) mbar_wait(empty + os, ((c / kTcOpStages) - 1) & 1);
-      const uint8_t* raw = s_raw + (size_t)(c % kTcRawStages) * kTcRawBytes;
-      uint8_t* ophi = s_op + (size_t)os * 2 * kTcOpBytes;
-      const float Cv = reinterpret_cast<const float*>(raw + (R6 + 1) * 128)[lane];
-      const float sq = (Cv > 0.f) ? 1.0f / sqrtf(Cv) : 0.f;               // sqrt(Q); zero-filled pixels beyond the range stay zero
-      const uint32_t col_off = (uint32_t)(lane & 3) * 4;
-      const uint32_t chunk16 = (uint32_t)(lane >> 2);
-#pragma unroll 4
-      for (int line = warp; line <= R6; line += kTcProducers / 32) {
-        const float x = reinterpret_cast<const float*>(raw + line * 128)[lane] * sq;
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-        const float hi = __uint_as_float(hb);
-        const float lo = x - hi;
-        const uint32_t off = (uint32_t)line * 128 + ((chunk16 ^ (uint32_t)(line & 7)) << 4) + col_off;
-        *reinterpret_cast<float*>(ophi + off) = hi;
-        *reinterpret_cast<float*>(ophi + kTcOpBytes + off) = lo;
+      TC_STAMP(dbg0, 16 + 8 * c + 2);
+      const uint32_t raw = raw_base + (uint32_t)(c % kTcRawStages) * kTcRawBytes + (uint32_t)warp * 2048 + (uint32_t)lane * 4;
+      const uint32_t ophi = op_base + (uint32_t)os * 2 * kTcOpBytes;
+      const float Cc[2] = {Cn0, Cn1};
+      Cn0 = load_c(c + 1, 0); Cn1 = packed ? load_c(c + 1, 1) : 0.f;      // one chunk ahead
+      const float sq0 = (Cc[0] > 0.f) ? rsqrtf(Cc[0]) : 0.f;           // sqrt(Q); pixels beyond the range stay zero
+      const float sq1 = (Cc[1] > 0.f) ? rsqrtf(Cc[1]) : 0.f;
+      float xv[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) xv[i] = lds_f32(raw + (uint32_t)i * 128);       // the whole slab first: 16 independent loads
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int hf = packed ? (i >> 3) : 0;
+        const int line = warp + 8 * (packed ? (i & 7) : i);
+        if (line <= R6) {                                               // warp-uniform
+          const uint32_t rr = (uint32_t)(hf * 64 + line);
+          const float x = xv[i] * (hf ? sq1 : sq0);
+          uint32_t hb;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+          const float hi = __uint_as_float(hb);
+          const uint32_t off = rr * 128 + ((sw_chunk ^ (rr & 7u)) << 4) + sw_col;
+          sts_f32(ophi + off, hi);
+          sts_f32(ophi + kTcOpBytes + off, x - hi);
+        }
       }
+      TC_STAMP(dbg0, 16 + 8 * c + 3);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy stores -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(full + os);
+      TC_STAMP(dbg0, 16 + 8 * c + 4);
       issue(c + kTcRawStages - 1);
+      TC_STAMP(dbg0, 16 + 8 * c + 5);
       if (c >= 2) drain(c - 2);
+      TC_STAMP(dbg0, 16 + 8 * c + 6);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (nchunks >= 2) drain(nchunks - 2);
     drain(nchunks - 1);
+    TC_STAMP(dbg0, 4);
+
+    // ================= G = hi lo^T: through shared memory (the operand ring is idle now) so that G + G^T can be formed
+    mbar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int cb = cb0 + h * 64;
+      if (h < ncb && cb < N && lq * 32 <= R6) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * 128 + cb), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j++) sts_f32(op_base + (uint32_t)(row * kTcCxStride + cb + j) * 4, __uint_as_float(r[j]));
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");
 
     // ================= epilogue: lower triangle of S (and the rhs column) into the reduced system =================
-    const int row = q * 32 + lane;
-    const int gr = s_gidx[row];
+    const int gr = (lrow < R6) ? s_gidx[lrow] : -2;
     if (gr >= 0) {
+      const int cofs = packed ? (row & 64) : 0;                     // first operand column of this row's half
 #pragma unroll
       for (int h = 0; h < 2; h++) {
-        const int cb = half * 32 + h * 64;
-        if (cb < N) {
+        const int cb = cb0 + h * 64;
+        if (h < ncb && cb < N) {
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            const int gc = s_gidx[cb + j];
-            const double v = -(double)acc[h][j];
+            const int col = cb + j;
+            const int gc = s_gidx[col - cofs];
+            if (gc == -2) continue;
+            const float g = lds_f32(op_base + (uint32_t)(row * kTcCxStride + col) * 4) + lds_f32(op_base + (uint32_t)(col * kTcCxStride + row) * 4);
+            const double v = -(double)(acc[h][j] + g);
             if (gc >= 0) {
               if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
-            } else if (gc == -1) {
+            } else {
               atomicAdd(&bsys[gr], v);
             }
           }
@@ -998,8 +1081,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
       }
     }
   }
+  TC_STAMP(dbg0, 5);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  TC_STAMP(dbg0, 6);
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
@@ -1203,9 +1288,9 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
     static const bool force_simt = (getenv("DBA_SCHUR_SIMT") != nullptr && getenv("DBA_SCHUR_SIMT")[0] == '1');
     const bool use_tc = (HW % 4 == 0) && !force_simt;
     if (use_tc) {
-      const int tiles32 = (HW + kTcK - 1) / kTcK;
-      const int chunks_tc = std::max(1, std::min(tiles32, (148 + eff_frames / 2) / eff_frames));     // one CTA per SM
-      const int px_per_cta_tc = ((tiles32 + chunks_tc - 1) / chunks_tc) * kTcK;
+      const int tiles64 = (HW + 63) / 64;
+      const int chunks_tc = std::max(1, std::min(tiles64, (148 + eff_frames / 2) / eff_frames));     // one CTA per SM
+      const int px_per_cta_tc = ((tiles64 + chunks_tc - 1) / chunks_tc) * 64;
       const int gx_tc = (HW + px_per_cta_tc - 1) / px_per_cta_tc;
       ba_schur_tc_kernel<<<dim3(gx_tc, a->n_frames, 1), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta_tc, WS(float, L.off_Eij),
@@ -1283,6 +1368,13 @@ extern "C" int dba_ba_p2p_signal(const dba_ba_args* a) {
   DBA_CHECK_LAUNCH("ba_p2p_signal");
   return DBA_OK;
 }
+
+#ifdef DBA_TC_TIMING
+extern "C" int dba_debug_tc_timing(unsigned long long* out, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out, dba::g_tc_timing, sizeof(unsigned long long) * (size_t)std::min(n, 8192));
+}
+#endif
 
 extern "C" int dba_ba(const dba_ba_args* a, int iterations) {
   int rc = dba_ba_prepare(a);
