@@ -193,17 +193,28 @@ def run_ours(args, rank, world, dev):
     use_graph = not args.no_graph and BA_ITERS % 2 == 0
     graph = None
     if use_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                spbox[0] = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-                step_resident()
-                spbox[0] = sp
-        torch.cuda.current_stream().wait_stream(side)
-        for _ in range(3):
-            graph.replay()
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    spbox[0] = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                    step_resident()
+                    spbox[0] = sp
+            torch.cuda.current_stream().wait_stream(side)
+            for _ in range(3):
+                graph.replay()
+        except Exception as e:                       # capture refused (e.g. a collective that cannot be captured): launch eagerly
+            sys.stderr.write("[bench] CUDA graph capture failed on rank %d, falling back to eager launches: %s\n" % (rank, str(e)[:200]))
+            spbox[0] = sp
+            graph = None
+            use_graph = False
+        if world > 1:                                # every rank replays the graph or none does
+            okf = torch.tensor([1.0 if graph is not None else 0.0], device=dev)
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+            if float(okf) == 0.0:
+                graph, use_graph = None, False
         barrier()
     sampler = ClockSampler(torch.cuda.current_device()); sampler.start()
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
