@@ -1,5 +1,6 @@
 """CPU tests (no GPU): the oracle against independent derivations, the synthetic generator, the C-ABI exports."""
 import ctypes
+import subprocess
 import math
 import os
 import re
@@ -268,6 +269,22 @@ def test_capi_exports_match_header():
     for name in sorted(declared):
         assert hasattr(L, name), name
     assert c_api.load().dba_version() >= 100
+
+
+def test_capi_args_struct_layout_matches_header(tmp_path):
+    """the ctypes mirror of dba_ba_args must have the C header's size and field offsets (the struct grows over time)"""
+    fields = [f[0] for f in c_api.BAArgs._fields_]
+    src = tmp_path / "layout.c"
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "droid_b200.h"', 'int main(void) {',
+            '  printf("%zu\\n", sizeof(dba_ba_args));']
+    prog += ['  printf("%%zu\\n", offsetof(dba_ba_args, %s));' % f for f in fields]
+    prog += ['  return 0; }']
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(c_api.BAArgs)
+    assert out[1:] == [getattr(c_api.BAArgs, f).offset for f in fields]
 
 
 def test_capi_argument_validation_without_gpu():
