@@ -128,7 +128,10 @@ def make_scene(cfg="metric", seed=0, rgbd=False, **over):
     xi = k * torch.tensor([0.05, 0.0, 0.02, 0.0, 0.01, 0.0], dtype=torch.float64) + 0.01 * torch.randn(N, 6, generator=g, dtype=torch.float64)
     poses_gt = se3_exp(xi)
     disps_gt = (1.0 + 0.3 * _smooth_noise(g, N, ht, wd)).clamp(0.1, 4.0)
-    ii, jj = make_graph(E, N, stereo=c.get("stereo", False), seed=seed)
+    if c.get("graph") is not None:                       # explicit edge list (ii, jj) instead of the generated sliding-window graph
+        ii, jj = (torch.as_tensor(x, dtype=torch.long) for x in c["graph"])
+    else:
+        ii, jj = make_graph(E, N, stereo=c.get("stereo", False), seed=seed)
     E = ii.shape[0]
     t0 = c.get("t0", 1); t1 = c.get("t1", N)
     coords, z_true = reproject(poses_gt, disps_gt, intr, ii, jj)

@@ -118,3 +118,33 @@ def test_stress_shape_72x96_bf16_and_ba(backends):
     oracle.ba(P64, D64, s["intrinsics"], s["disps_sens"], s["targets"], s["weights"], s["eta"], s["ii"], s["jj"], s["t0"], s["t1"], 2,
               s["lm"], s["ep"], False, dtype=torch.float64)
     assert rel_err(P, P64, floor=1.0) < 1e-4 and rel_err(D, D64, floor=1.0) < 1e-4
+
+
+def _mixed_degree_graph(N=34):
+    """frames with 3-5 rows (packed tensor-core tiles), 16 rows (one tile per 32 pixels) and 25 rows (CUDA-core tile pairs),
+    plus a duplicated edge: every Schur kernel and the duplicate-pose rule (both (r,c) and (c,r) land on one diagonal block).
+    The extra edges stay within 12 frames so that the problem is as well conditioned as a covisibility graph."""
+    e = []
+    for i in range(N):
+        for j in (i - 2, i - 1, i + 1, i + 2):
+            if 0 <= j < N:
+                e.append((i, j))
+    e += [(17, j) for j in range(5, 30) if abs(j - 17) > 2]           # frame 17: 24 out-edges -> 25 rows
+    e += [(26, j) for j in range(18, 34) if abs(j - 26) > 2]          # frame 26: 15 out-edges -> 16 rows
+    e += [(9, 10)]                                                     # duplicate of an existing edge
+    return [a for a, _ in e], [b for _, b in e]
+
+
+def test_ba_every_schur_kernel_matches_oracle(backends):
+    ii, jj = _mixed_degree_graph()
+    s = synth.make_scene(dict(E=len(ii), N=34, ht=48, wd=64, stereo=False, itrs=2, lm=1e-4, ep=0.1, graph=(ii, jj)), seed=1)
+    deg = torch.bincount(s["ii"], minlength=34)
+    assert int(deg[17]) == 24 and int(deg[26]) == 15 and int(deg.min()) >= 2
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    P, D = s["poses"].to(dev), s["disps"].to(dev)
+    args = [s[k].to(dev) for k in ("intrinsics", "disps_sens", "targets", "weights", "eta", "ii", "jj")]
+    backends.ba(P, D, *args, s["t0"], s["t1"], 2, s["lm"], s["ep"], False)
+    P64, D64 = s["poses"].double(), s["disps"].double()
+    oracle.ba(P64, D64, s["intrinsics"], s["disps_sens"], s["targets"], s["weights"], s["eta"], s["ii"], s["jj"], s["t0"], s["t1"], 2,
+              s["lm"], s["ep"], False, dtype=torch.float64)
+    assert rel_err(P, P64, floor=1.0) < 1e-4 and rel_err(D, D64, floor=1.0) < 1e-4
