@@ -505,6 +505,7 @@ __global__ void __launch_bounds__(kSgThreads) ba_schur_gemm_kernel(
   __shared__ float sQw[kSgK];
   __shared__ float sQ[kSgK];
 
+  if (deg + 1 <= min_rows) return;                     // at most deg + 1 rows: not this kernel's frame (skips the row-list build)
   build_row_list<kSgThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
   const int nrows = s_nrows;
   if (nrows <= min_rows) return;                       // smaller frames belong to ba_schur_tc_kernel / ba_schur_small_kernel
@@ -928,12 +929,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
     for (int i = 0; i < 4; i++) {
       const int li = 4 * i + (lane >> 3), piece = lane & 7;
       const int hf = packed ? (li >> 3) : 0, line = warp + 8 * (packed ? (li & 7) : li);
-      src[i] = nullptr; dst[i] = 0; pxo[i] = 0;
+      // slots without a line copy zero bytes (cp.async zero-fills) into their unused slab row: no branch in the copy loop
+      src[i] = Cin; pxo[i] = 1 << 30;
+      dst[i] = raw_base + warp * 2048 + li * 128 + piece * 16;
       if (line <= R6) {
         const float* base = (line < R6) ? s_ptr[line / 6] + (size_t)(line % 6) * HW : win + (size_t)m * HW;
         pxo[i] = hf * 32 + piece * 4;
         src[i] = base + pxo[i];
-        dst[i] = raw_base + warp * 2048 + li * 128 + piece * 16;
       }
     }
     const float* Cm = Cin + (size_t)m * HW;
@@ -975,10 +977,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
         const uint32_t stage_off = (uint32_t)(c % kTcRawStages) * kTcRawBytes;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          if (src[i] != nullptr) {
-            const bool ok = p0 + pxo[i] < px_end;
-            cp_async16_zfill(dst[i] + stage_off, ok ? (const void*)(src[i] + p0) : (const void*)Cin, ok ? 16u : 0u);
-          }
+          const bool ok = p0 + pxo[i] < px_end;            // false for slots without a line (pxo = 2^30)
+          cp_async16_zfill(dst[i] + stage_off, ok ? (const void*)(src[i] + p0) : (const void*)Cin, ok ? 16u : 0u);
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -1010,20 +1010,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
       float xv[16];
 #pragma unroll
       for (int i = 0; i < 16; i++) xv[i] = lds_f32(raw + (uint32_t)i * 128);       // the whole slab first: 16 independent loads
+      // straight-line split of all 16 slab rows (16-way instruction-level parallelism; a branch per row would serialise the
+      // dependent scale -> round -> subtract chains), then predicated stores of the live rows
+      float hv[16], lv[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const float x = xv[i] * ((packed && i >= 8) ? sq1 : sq0);
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+        hv[i] = __uint_as_float(hb);
+        lv[i] = x - hv[i];
+      }
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         const int hf = packed ? (i >> 3) : 0;
         const int line = warp + 8 * (packed ? (i & 7) : i);
-        if (line <= R6) {                                               // warp-uniform
-          const uint32_t rr = (uint32_t)(hf * 64 + line);
-          const float x = xv[i] * (hf ? sq1 : sq0);
-          uint32_t hb;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-          const float hi = __uint_as_float(hb);
-          const uint32_t off = rr * 128 + ((sw_chunk ^ (rr & 7u)) << 4) + sw_col;
-          sts_f32(ophi + off, hi);
-          sts_f32(ophi + kTcOpBytes + off, x - hi);
-        }
+        const uint32_t rr = (uint32_t)(hf * 64 + line);
+        const uint32_t off = rr * 128 + ((sw_chunk ^ (rr & 7u)) << 4) + sw_col;
+        if (line <= R6) { sts_f32(ophi + off, hv[i]); sts_f32(ophi + kTcOpBytes + off, lv[i]); }      // warp-uniform predicate
       }
       TC_STAMP(dbg0, 16 + 8 * c + 3);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy stores -> visible to the tensor core
