@@ -884,6 +884,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
   const uint32_t tmem_base = *tmem_base_smem;
   const bool dbg = (blockIdx.x == 0 && blockIdx.y == 20);
   const bool dbg0 = dbg && tid == 0;
+  (void)dbg0;
   TC_STAMP(dbg0, 0);
 #ifdef DBA_TC_TIMING
   if (dbg0) { g_tc_timing[1] = (unsigned long long)nchunks; g_tc_timing[2] = (unsigned long long)R6; }
@@ -986,12 +987,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
 #pragma unroll
     for (int s = 0; s < kTcRawStages - 1; s++) issue(s);
 
-    const uint32_t sw_col = (uint32_t)(lane & 3) * 4, sw_chunk = (uint32_t)(lane >> 2);
-    auto load_c = [&](int c, int hf) -> float {            // C of this lane's pixel in half hf of chunk c (0 beyond the range)
-      const int px = px_begin + c * cpx + hf * 32 + lane;
-      return (c < nchunks && px < px_end) ? __ldg(Cm + px) : 0.f;
+    // A thread splits exactly the 16-byte pieces it copied (slot i: slab row 4 i + lane / 8, pixels 4 (lane % 8) .. + 3): one
+    // 128-bit shared load, four scale / round / subtract chains, two 128-bit swizzled stores per slot.  A 16-byte piece stays
+    // contiguous under the 128-byte swizzle (chunk index ^ row % 8).
+    const int piece = lane & 7;
+    uint32_t op_off[4];                                      // byte offset of the slot's piece inside an operand tile
+    bool live[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int li = 4 * i + (lane >> 3);
+      const int hf = packed ? (li >> 3) : 0, line = warp + 8 * (packed ? (li & 7) : li);
+      const uint32_t rr = (uint32_t)(hf * 64 + line);
+      live[i] = line <= R6;
+      op_off[i] = rr * 128 + (((uint32_t)piece ^ (rr & 7u)) << 4);
+    }
+    auto load_c4 = [&](int c, int hf) -> float4 {          // C of this thread's four pixels in half hf of chunk c (0 beyond the range)
+      const int px = px_begin + c * cpx + hf * 32 + 4 * piece;
+      return (c < nchunks && px < px_end) ? __ldg(reinterpret_cast<const float4*>(Cm + px)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    float Cn0 = load_c(0, 0), Cn1 = packed ? load_c(0, 1) : 0.f;
+    auto rsq4 = [](float4 v) -> float4 {                     // sqrt(Q); pixels beyond the range stay zero
+      return make_float4(v.x > 0.f ? rsqrtf(v.x) : 0.f, v.y > 0.f ? rsqrtf(v.y) : 0.f, v.z > 0.f ? rsqrtf(v.z) : 0.f, v.w > 0.f ? rsqrtf(v.w) : 0.f);
+    };
+    float4 Cn0 = load_c4(0, 0), Cn1 = packed ? load_c4(0, 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     TC_STAMP(dbg0, 3);
     for (int c = 0; c < nchunks; c++) {
       TC_STAMP(dbg0, 16 + 8 * c + 0);
@@ -1001,33 +1018,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
       const int os = c % kTcOpStages;
       if (c >= kTcOpStages) mbar_wait(empty + os, ((c / kTcOpStages) - 1) & 1);
       TC_STAMP(dbg0, 16 + 8 * c + 2);
-      const uint32_t raw = raw_base + (uint32_t)(c % kTcRawStages) * kTcRawBytes + (uint32_t)warp * 2048 + (uint32_t)lane * 4;
+      const uint32_t raw = raw_base + (uint32_t)(c % kTcRawStages) * kTcRawBytes + (uint32_t)warp * 2048 + (uint32_t)(lane >> 3) * 128 +
+                           (uint32_t)piece * 16;
       const uint32_t ophi = op_base + (uint32_t)os * 2 * kTcOpBytes;
-      const float Cc[2] = {Cn0, Cn1};
-      Cn0 = load_c(c + 1, 0); Cn1 = packed ? load_c(c + 1, 1) : 0.f;      // one chunk ahead
-      const float sq0 = (Cc[0] > 0.f) ? rsqrtf(Cc[0]) : 0.f;           // sqrt(Q); pixels beyond the range stay zero
-      const float sq1 = (Cc[1] > 0.f) ? rsqrtf(Cc[1]) : 0.f;
-      float xv[16];
+      const float4 sq0 = rsq4(Cn0), sq1 = rsq4(Cn1);
+      Cn0 = load_c4(c + 1, 0); Cn1 = packed ? load_c4(c + 1, 1) : Cn1;      // one chunk ahead
+      float4 xv[4];
 #pragma unroll
-      for (int i = 0; i < 16; i++) xv[i] = lds_f32(raw + (uint32_t)i * 128);       // the whole slab first: 16 independent loads
-      // straight-line split of all 16 slab rows (16-way instruction-level parallelism; a branch per row would serialise the
-      // dependent scale -> round -> subtract chains), then predicated stores of the live rows
-      float hv[16], lv[16];
+      for (int i = 0; i < 4; i++)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(xv[i].x), "=f"(xv[i].y), "=f"(xv[i].z), "=f"(xv[i].w) : "r"(raw + (uint32_t)i * 512) : "memory");
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const float x = xv[i] * ((packed && i >= 8) ? sq1 : sq0);
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-        hv[i] = __uint_as_float(hb);
-        lv[i] = x - hv[i];
-      }
+      for (int i = 0; i < 4; i++) {
+        const float4 q = (packed && i >= 2) ? sq1 : sq0;
+        const float x[4] = {xv[i].x * q.x, xv[i].y * q.y, xv[i].z * q.z, xv[i].w * q.w};
+        float hi[4], lo[4];
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const int hf = packed ? (i >> 3) : 0;
-        const int line = warp + 8 * (packed ? (i & 7) : i);
-        const uint32_t rr = (uint32_t)(hf * 64 + line);
-        const uint32_t off = rr * 128 + ((sw_chunk ^ (rr & 7u)) << 4) + sw_col;
-        if (line <= R6) { sts_f32(ophi + off, hv[i]); sts_f32(ophi + kTcOpBytes + off, lv[i]); }      // warp-uniform predicate
+        for (int k = 0; k < 4; k++) {                        // tf32 round-to-nearest (ties away), as cvt.rna.tf32.f32 for finite x
+          hi[k] = __uint_as_float((__float_as_uint(x[k]) + 0x1000u) & 0xffffe000u);
+          lo[k] = x[k] - hi[k];
+        }
+        if (live[i]) {
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ophi + op_off[i]), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(ophi + kTcOpBytes + op_off[i]), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "f"(lo[3]) : "memory");
+        }
       }
       TC_STAMP(dbg0, 16 + 8 * c + 3);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // generic-proxy stores -> visible to the tensor core

@@ -185,11 +185,17 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       } else if (r == nt * kT && c < n) src = nn + c;
       if (src != (size_t)-1) {
         if (world > 1) {
-          for (int q = 0; q < world; q++) {             // fixed rank order: every rank computes the identical sum
-            double t;
-            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t) : "l"(p.peers.sys[q] + src) : "memory");
-            v += t;
+          // all peer loads are issued before the first add (the NVLink round trips overlap), then summed in fixed rank order:
+          // every rank computes the identical sum
+          double t[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            t[q] = 0.0;
+            if (q < world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t[q]) : "l"(p.peers.sys[q] + src) : "memory");
           }
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+            if (q < world) v += t[q];
         } else v = (src < nn) ? p.H[src] : p.b[src - nn];
         if (src < nn && r == c) v += p.ep + p.lm * v;
       }

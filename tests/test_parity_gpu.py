@@ -329,3 +329,46 @@ def test_fused_reproject_matches_projective_transform_restatement(backends):
     assert c.shape == (1, 30, 16, 24, 2) and v.shape == (1, 30, 16, 24, 1)
     assert rel_err(c[0], rc, floor=1.0) < 1e-4 and frac_equal(v[0], rv) > 0.999
     assert 0.05 < float(rv.mean()) < 1.0 and bool((s["ii"] == s["jj"]).any())
+
+
+def test_fused_p2p_reduction_two_virtual_ranks_on_one_gpu(backends):
+    """The cross-GPU reduction fused into the Cholesky kernel, exercised on ONE device: two edge shards
+    ("ranks") build their partial pose systems into two buffers that play the role of peer memory, publish their epochs, and each
+    rank's solve sums both copies itself.  Result must match the unsharded BA and be identical on both ranks."""
+    from droid_slam_b200 import sharded
+
+    class VirtualPeer:                       # what sharded.P2PSystem provides, without symmetric memory
+        def __init__(self, nd, ptrs, rank):
+            self.nd, self.ptrs, self.world, self.rank, self.epoch = nd, ptrs, len(ptrs), rank, 0
+            self.epoch_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    s = synth.make_scene("c2_frontend")
+    N, ht, wd = s["disps"].shape
+    n = 6 * (s["t1"] - s["t0"]); nd = n * n + n
+    bufs = [torch.zeros(2 * nd + 8, dtype=torch.float64, device=dev) for _ in range(2)]
+    ptrs = [b.data_ptr() for b in bufs]
+    bounds = sharded.partition_frames(s["ii"], N, 2)
+    kx = torch.unique(torch.cat([torch.arange(s["t0"], s["t1"]), s["ii"]]))
+    eta_f = torch.zeros(N, ht, wd); eta_f[kx] = s["eta"]
+    common = [s[k].to(dev) for k in ("intrinsics", "disps_sens")]
+    ranks = []
+    for r in range(2):
+        idx = sharded.shard_edges(s["ii"], *bounds[r])
+        st = dict(P=s["poses"].to(dev), D=s["disps"].to(dev), tg=s["targets"][idx].contiguous().to(dev), wt=s["weights"][idx].contiguous().to(dev),
+                  ii=s["ii"][idx].contiguous().to(dev), jj=s["jj"][idx].contiguous().to(dev), eta=eta_f.to(dev))
+        eng = sharded.CApiEngine(dev)
+        eng.setup(st["P"], st["D"], common[0], common[1], st["tg"], st["wt"], st["eta"], st["ii"], st["jj"], s["t0"], s["t1"], s["lm"], s["ep"],
+                  bounds[r], p2p=VirtualPeer(nd, ptrs, r))
+        ranks.append((eng, st))
+    for _ in range(2):
+        for eng, _ in ranks: eng.build()
+        for eng, _ in ranks: eng.publish()
+        for eng, _ in ranks: eng.solve()
+    torch.cuda.synchronize()
+    (e0, s0), (e1, s1) = ranks
+    assert torch.equal(s0["P"], s1["P"]) and torch.equal(e0.dx, e1.dx)                 # replicated solve: bit-identical on both ranks
+    D = torch.cat([s0["D"][:bounds[0][1]], s1["D"][bounds[1][0]:]])
+    P1, D1 = s["poses"].to(dev), s["disps"].to(dev)
+    args = [s[k].to(dev) for k in ("intrinsics", "disps_sens", "targets", "weights", "eta", "ii", "jj")]
+    backends.ba(P1, D1, *args, s["t0"], s["t1"], 2, s["lm"], s["ep"], False)
+    assert float((s0["P"] - P1).abs().max()) < 2e-5 and float((D - D1).abs().max()) < 5e-5
