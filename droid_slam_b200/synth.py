@@ -185,3 +185,37 @@ def make_corr_inputs(scene, dtype=torch.float16, seed=0, channels=128, device="c
             if l + 1 < levels:
                 corr = F.avg_pool2d(corr, 2, stride=2)
     return pyr, coords, fmaps
+
+
+# ---- update operator: weights with the reference's state_dict names and shapes (droid_net.py:79-109,
+# modules/gru.py:9-17, droid_net.py:46-57), drawn from a seed so that the reference module, the oracle and the mirror share them
+UPDATE_SHAPES = {
+    "corr_encoder.0": (128, 196, 1), "corr_encoder.2": (128, 128, 3),
+    "flow_encoder.0": (128, 4, 7), "flow_encoder.2": (64, 128, 3),
+    "weight.0": (128, 128, 3), "weight.2": (2, 128, 3),
+    "delta.0": (128, 128, 3), "delta.2": (2, 128, 3),
+    "gru.convz": (128, 448, 3), "gru.convr": (128, 448, 3), "gru.convq": (128, 448, 3), "gru.w": (128, 128, 1),
+    "gru.convz_glo": (128, 128, 1), "gru.convr_glo": (128, 128, 1), "gru.convq_glo": (128, 128, 1),
+    "agg.conv1": (128, 128, 3), "agg.conv2": (128, 128, 3), "agg.eta.0": (1, 128, 3), "agg.upmask.0": (576, 128, 1),
+}
+
+
+def make_update_weights(seed=0, dtype=torch.float32):
+    """He-scaled random weights + small biases for every conv of the update operator, keyed like UpdateModule.state_dict()."""
+    g = torch.Generator().manual_seed(4321 + seed)
+    w = {}
+    for name, (co, ci, k) in UPDATE_SHAPES.items():
+        w[name + ".weight"] = (torch.randn(co, ci, k, k, generator=g) * (1.0 / (ci * k * k)) ** 0.5).to(dtype)
+        w[name + ".bias"] = (0.1 * torch.randn(co, generator=g)).to(dtype)
+    return w
+
+
+def make_update_inputs(E=5, ht=6, wd=8, seed=0, n_src=3):
+    """net/inp/corr/flow of E edges at ht x wd and source-frame indices ii with n_src distinct (unsorted) values."""
+    g = torch.Generator().manual_seed(99 + seed)
+    net = torch.tanh(torch.randn(1, E, 128, ht, wd, generator=g))
+    inp = torch.relu(torch.randn(1, E, 128, ht, wd, generator=g))
+    corr = torch.randn(1, E, 196, ht, wd, generator=g)
+    flow = 4.0 * torch.randn(1, E, 4, ht, wd, generator=g)
+    ii = torch.randint(0, n_src, (E,), generator=g) * 3 + 2          # unsorted, non-contiguous frame numbers
+    return net, inp, corr, flow, ii

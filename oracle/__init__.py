@@ -17,3 +17,4 @@ from .se3 import *      # noqa: F401,F403
 from .geom import *     # noqa: F401,F403
 from .ba import *       # noqa: F401,F403
 from .corr import *     # noqa: F401,F403
+from .update import *   # noqa: F401,F403
