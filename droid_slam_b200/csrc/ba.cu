@@ -838,6 +838,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
   __shared__ int s_gidx[128];                     // operand row / column -> index in the reduced system (-1: rhs, -2: padding)
   extern __shared__ uint8_t tc_smem_raw[];
 
+  if (deg == 0) return;                           // no out-edge (e.g. a frame another rank owns): E_k = 0, nothing to subtract
   build_row_list<kTcThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
   const int nrows = s_nrows;
   if (nrows == 0 || nrows > kTcRowsMax) return;         // larger frames belong to ba_schur_gemm_kernel
