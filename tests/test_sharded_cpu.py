@@ -111,3 +111,28 @@ def test_sharded_ba_world2_matches_single_process():
         assert (disps - D).abs().max() < 1e-9                      # owners' depths exchanged after the last iteration
         assert 0 < ne < 36
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+
+
+# ---- property tests of the partitioning host logic (hypothesis) --------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 40), st.integers(1, 8), st.lists(st.integers(0, 39), min_size=0, max_size=200))
+def test_partition_properties(n_frames, world, src):
+    ii = torch.tensor([s % n_frames for s in src], dtype=torch.long)
+    b = sharded.partition_frames(ii, n_frames, world)
+    assert len(b) == world and b[0][0] == 0 and b[-1][1] == n_frames
+    assert all(lo <= hi for lo, hi in b) and all(b[r][1] == b[r + 1][0] for r in range(world - 1))       # contiguous, ordered, complete
+    assert b == sharded.partition_frames(ii.clone(), n_frames, world)                                      # deterministic (every rank computes it)
+    shards = [sharded.shard_edges(ii, lo, hi) for lo, hi in b]
+    allidx = torch.cat(shards) if shards else torch.zeros(0, dtype=torch.long)
+    assert sorted(allidx.tolist()) == list(range(ii.numel()))                                              # every edge owned exactly once
+    for (lo, hi), idx in zip(b, shards):
+        assert torch.equal(idx, torch.sort(idx).values)                                                    # original edge order kept
+        assert bool(((ii[idx] >= lo) & (ii[idx] < hi)).all())
+    if ii.numel() and world > 1:
+        deg = torch.bincount(ii, minlength=n_frames)
+        counts = [int(i.numel()) for i in shards]
+        # greedy prefix cuts: no shard exceeds its fair share by more than one frame's out-degree (+1 for the cut rule)
+        assert max(counts) <= ii.numel() / world + int(deg.max()) + 1
