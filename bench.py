@@ -480,6 +480,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if args.impl == "reference":
+        # the reference has no multi-GPU path: rank 0 alone measures it, the other ranks of a torchrun launch exit without work
+        # (no process group is created, so nothing can wait on anything)
+        if rank == 0:
+            run_reference(args, 0, 1, dev)
+        return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner at INFO/VERSION)
