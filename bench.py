@@ -357,9 +357,43 @@ def run_ours(args, rank, world, dev):
                      "traffic": (traffic or {}).get("dram_bytes_per_step_" + args.dtype)},
         "ba_ms_per_step": ms_step - corr_ms,
     }
+    if world == 1:
+        line["update_operator"] = update_operator_library_ms(E, dev, ms_step)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(pb)
     print(json.dumps(line))
+
+
+def update_operator_library_ms(E, dev, ms_step, iters=5):
+    """the full update = this step + the update operator.  The operator here is the LIBRARY baseline of row A6
+    (droid_slam_b200/update.py: torch/cuDNN convolutions under fp16 autocast like factor_graph.py:214), reported for context only --
+    it is not one of this repo's kernels and is not part of `value`.  Any failure is reported, never raised."""
+    try:
+        from droid_slam_b200 import synth
+        from droid_slam_b200.update import UpdateModule
+        mod = UpdateModule().to(dev).eval()
+        mod.load_state_dict({k: v.to(dev) for k, v in synth.make_update_weights(0).items()})
+        g = torch.Generator(device=dev).manual_seed(7)
+        net = torch.tanh(torch.randn(1, E, 128, HT, WD, generator=g, device=dev)).half()
+        inp = torch.relu(torch.randn(1, E, 128, HT, WD, generator=g, device=dev)).half()
+        corr = torch.randn(1, E, 196, HT, WD, generator=g, device=dev).half()
+        motn = torch.randn(1, E, 4, HT, WD, generator=g, device=dev)
+        ii = torch.arange(E, device=dev) % FRAMES
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            for _ in range(2):
+                mod(net, inp, corr, motn, ii)
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(iters):
+                mod(net, inp, corr, motn, ii)
+            ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / iters
+        return {"ms": ms, "full_update_ms": ms + ms_step, "edges": E,
+                "impl": "library baseline (torch/cuDNN convolutions, fp16 autocast); not a hand-written kernel, not included in value"}
+    except Exception as e:                                   # context only: never fail the bench line
+        return {"ms": None, "error": str(e)[:200]}
 
 
 # ---------------------------------------------------------------------------------------------------------
