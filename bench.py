@@ -165,7 +165,15 @@ def run_ours(args, rank, world, dev):
     engine = sharded.CApiEngine(dev)
     p2p = None
     if world > 1 and args.collective == "p2p":
-        p2p = sharded.P2PSystem(6 * (pb["t1"] - pb["t0"]), dev)
+        try:
+            p2p = sharded.P2PSystem(6 * (pb["t1"] - pb["t0"]), dev)
+        except Exception as e:                       # no peer-mapped memory on this box: plain NCCL all-reduce of the pose system
+            sys.stderr.write("[bench] rank %d: symmetric memory unavailable (%s); using the NCCL all-reduce path\n" % (rank, str(e)[:160]))
+            p2p = None
+        okp = torch.tensor([1.0 if p2p is not None else 0.0], device=dev)
+        dist.all_reduce(okp, op=dist.ReduceOp.MIN)   # all ranks take the same path
+        if float(okp) == 0.0:
+            p2p = None
     drv = sharded.ShardedBA(engine, p2p=p2p)
 
     def step_resident(ev=None):
