@@ -19,6 +19,13 @@ import torch.nn.functional as F
 __all__ = ["ConvGRU", "GraphAgg", "UpdateModule", "segment_mean"]
 
 
+def _conv(name):
+    """the convolution `name` of the update operator with the reference's shape (table in synth.UPDATE_SHAPES), 'same' padding"""
+    from .synth import UPDATE_SHAPES
+    co, ci, k = UPDATE_SHAPES[name]
+    return nn.Conv2d(ci, co, k, padding=k // 2)
+
+
 def segment_mean(x, ii):
     """mean over dim 1 of the entries with equal ii; slots ordered by ascending ii (== scatter_mean(x, unique_inverse(ii), dim=1))"""
     uniq, ix = torch.unique(ii, return_inverse=True)
@@ -31,15 +38,10 @@ def segment_mean(x, ii):
 class ConvGRU(nn.Module):
     """modules/gru.py:5-32 (same parameter names)"""
 
-    def __init__(self, h_planes=128, i_planes=128):
+    def __init__(self, prefix="gru."):
         super().__init__()
-        self.convz = nn.Conv2d(h_planes + i_planes, h_planes, 3, padding=1)
-        self.convr = nn.Conv2d(h_planes + i_planes, h_planes, 3, padding=1)
-        self.convq = nn.Conv2d(h_planes + i_planes, h_planes, 3, padding=1)
-        self.w = nn.Conv2d(h_planes, h_planes, 1, padding=0)
-        self.convz_glo = nn.Conv2d(h_planes, h_planes, 1, padding=0)
-        self.convr_glo = nn.Conv2d(h_planes, h_planes, 1, padding=0)
-        self.convq_glo = nn.Conv2d(h_planes, h_planes, 1, padding=0)
+        for name in ("convz", "convr", "convq", "w", "convz_glo", "convr_glo", "convq_glo"):      # shapes: synth.UPDATE_SHAPES
+            setattr(self, name, _conv(prefix + name))
 
     def forward(self, net, *inputs):
         inp = torch.cat(inputs, dim=1)
@@ -61,12 +63,11 @@ class ConvGRU(nn.Module):
 class GraphAgg(nn.Module):
     """droid_net.py:46-75 (same parameter names; GradientClip is the identity in the forward pass and has no parameters)"""
 
-    def __init__(self):
+    def __init__(self, prefix="agg."):
         super().__init__()
-        self.conv1 = nn.Conv2d(128, 128, 3, padding=1)
-        self.conv2 = nn.Conv2d(128, 128, 3, padding=1)
-        self.eta = nn.Sequential(nn.Conv2d(128, 1, 3, padding=1), nn.Identity(), nn.Softplus())
-        self.upmask = nn.Sequential(nn.Conv2d(128, 8 * 8 * 9, 1, padding=0))
+        self.conv1, self.conv2 = _conv(prefix + "conv1"), _conv(prefix + "conv2")
+        self.eta = nn.Sequential(_conv(prefix + "eta.0"), nn.Identity(), nn.Softplus())          # slot 1: the reference's GradientClip
+        self.upmask = nn.Sequential(_conv(prefix + "upmask.0"))
 
     def forward(self, net, ii):
         batch, num, ch, ht, wd = net.shape
@@ -83,16 +84,12 @@ class UpdateModule(nn.Module):
 
     def __init__(self):
         super().__init__()
-        cor_planes = 4 * (2 * 3 + 1) ** 2
-        self.corr_encoder = nn.Sequential(nn.Conv2d(cor_planes, 128, 1, padding=0), nn.ReLU(inplace=True),
-                                          nn.Conv2d(128, 128, 3, padding=1), nn.ReLU(inplace=True))
-        self.flow_encoder = nn.Sequential(nn.Conv2d(4, 128, 7, padding=3), nn.ReLU(inplace=True),
-                                          nn.Conv2d(128, 64, 3, padding=1), nn.ReLU(inplace=True))
-        self.weight = nn.Sequential(nn.Conv2d(128, 128, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(128, 2, 3, padding=1),
-                                    nn.Identity(), nn.Sigmoid())
-        self.delta = nn.Sequential(nn.Conv2d(128, 128, 3, padding=1), nn.ReLU(inplace=True), nn.Conv2d(128, 2, 3, padding=1),
-                                   nn.Identity())
-        self.gru = ConvGRU(128, 128 + 128 + 64)
+        relu = lambda: nn.ReLU(inplace=True)
+        self.corr_encoder = nn.Sequential(_conv("corr_encoder.0"), relu(), _conv("corr_encoder.2"), relu())
+        self.flow_encoder = nn.Sequential(_conv("flow_encoder.0"), relu(), _conv("flow_encoder.2"), relu())
+        self.weight = nn.Sequential(_conv("weight.0"), relu(), _conv("weight.2"), nn.Identity(), nn.Sigmoid())
+        self.delta = nn.Sequential(_conv("delta.0"), relu(), _conv("delta.2"), nn.Identity())
+        self.gru = ConvGRU()
         self.agg = GraphAgg()
 
     def forward(self, net, inp, corr, flow=None, ii=None, jj=None):
