@@ -18,8 +18,9 @@ EXTDIR = os.path.join(PKG, "_ext")
 OBJDIR = os.path.join(PKG, "build")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
-NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CUDA_SOURCES = ["common.cu", "corr_index.cu", "altcorr.cu", "geom.cu", "ba.cu", "chol.cu", "corr_volume.cu"]
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+NVCC = os.environ.get("NVCC", os.path.join(CUDA_HOME, "bin", "nvcc"))
+CUDA_SOURCES = ["common.cu", "corr_index.cu", "altcorr.cu", "geom.cu", "ba.cu", "chol.cu", "corr_volume.cu", "update_op.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177"]
 
@@ -74,12 +75,12 @@ def build_binding(verbose=False):
     tinc = os.path.join(tdir, "include")
     tlib = os.path.join(tdir, "lib")
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=droid_backends",
-           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=1",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI),
            "-I" + tinc, "-I" + os.path.join(tinc, "torch", "csrc", "api", "include"),
-           "-I" + sysconfig.get_paths()["include"], "-I/usr/local/cuda/include",
+           "-I" + sysconfig.get_paths()["include"], "-I" + os.path.join(CUDA_HOME, "include"),
            src, "-o", EXT_PATH,
            "-L" + LIBDIR, "-ldroid_b200", "-L" + tlib, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
-           "-ltorch_python", "-L/usr/local/cuda/lib64", "-lcudart",
+           "-ltorch_python", "-L" + os.path.join(CUDA_HOME, "lib64"), "-lcudart",
            "-Wl,-rpath,$ORIGIN/../lib", "-Wl,-rpath," + tlib]
     out = _run(cmd)
     if verbose and out.strip():

@@ -11,6 +11,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <vector>
+#include <cstring>
 #include "../../../include/droid_b200.h"
 
 #define CHECK_CONTIGUOUS(x) TORCH_CHECK(x.is_contiguous(), #x " must be contiguous")   // reference src/droid.cpp:89
@@ -247,6 +248,85 @@ std::vector<torch::Tensor> reproject(torch::Tensor poses, torch::Tensor disps, t
   return {coords, valid};
 }
 
+// extension: the update operator (reference droid_slam/droid_net.py:111-143, modules/gru.py:19-32, droid_net.py:59-75) on the tensor
+// cores.  net [E,128,ht,wd] f16/f32 (or channels-last f16 [E,ht,wd,128] when net_channels_last), inp [E,128,ht,wd], corr [E,196,ht,wd],
+// flow [E,4,ht,wd] f32 or None, seg [E] int64 (torch.unique inverse of the source frames) or None, n_src distinct sources,
+// packed = the 26 tensors of droid_slam_b200.update.pack_update_weights in dba_update_weights order.
+// Returns [net' (channels-last f16 [E,ht,wd,128]), delta [E,ht,wd,2] f32, weight [E,ht,wd,2] f32 (, eta [n_src,ht,wd] f32, upmask [n_src,576,ht,wd] f16)].
+std::vector<torch::Tensor> update_forward(torch::Tensor net, torch::Tensor inp, torch::Tensor corr, c10::optional<torch::Tensor> flow,
+                                          c10::optional<torch::Tensor> seg, int64_t n_src, std::vector<torch::Tensor> packed, bool net_channels_last) {
+  CHECK_INPUT(net); CHECK_INPUT(inp); CHECK_INPUT(corr);
+  TORCH_CHECK(net.dim() == 4 && inp.dim() == 4 && corr.dim() == 4, "net/inp/corr must be 4-D");
+  TORCH_CHECK(packed.size() == 26, "packed weights: 26 tensors expected");
+  c10::cuda::CUDAGuard guard(net.device());
+  int E, ht, wd;
+  if (net_channels_last) {
+    TORCH_CHECK(net.scalar_type() == torch::kFloat16 && net.size(3) == 128, "channels-last net must be f16 [E,ht,wd,128]");
+    E = (int)net.size(0); ht = (int)net.size(1); wd = (int)net.size(2);
+  } else {
+    TORCH_CHECK(net.size(1) == 128, "net must be [E,128,ht,wd]");
+    E = (int)net.size(0); ht = (int)net.size(2); wd = (int)net.size(3);
+  }
+  TORCH_CHECK(inp.size(0) == E && inp.size(1) == 128 && inp.size(2) == ht && inp.size(3) == wd, "inp must be [E,128,ht,wd]");
+  TORCH_CHECK(corr.size(0) == E && corr.size(1) == 196 && corr.size(2) == ht && corr.size(3) == wd, "corr must be [E,196,ht,wd]");
+  torch::Tensor flow_c, seg_c;
+  if (flow.has_value() && flow->defined()) {
+    flow_c = flow->to(torch::kFloat32).contiguous();
+    CHECK_CUDA(flow_c);
+    TORCH_CHECK(flow_c.numel() == (int64_t)E * 4 * ht * wd, "flow must be [E,4,ht,wd]");
+  }
+  const bool agg = seg.has_value() && seg->defined() && n_src > 0;
+  if (agg) { seg_c = seg->contiguous(); CHECK_CUDA(seg_c); CHECK_I64(seg_c); TORCH_CHECK(seg_c.numel() == E, "seg must have one entry per edge"); }
+  dba_update_weights W;
+  const void** wp = reinterpret_cast<const void**>(&W);
+  for (int k = 0; k < 26; k++) {
+    CHECK_INPUT(packed[k]);
+    TORCH_CHECK(packed[k].scalar_type() == (k < 12 ? torch::kFloat16 : torch::kFloat32), "packed weight ", k, " has the wrong dtype");
+    wp[k] = packed[k].data_ptr();
+  }
+  auto o16 = torch::TensorOptions().dtype(torch::kFloat16).device(net.device());
+  auto o32 = torch::TensorOptions().dtype(torch::kFloat32).device(net.device());
+  auto net_out = torch::empty({E, ht, wd, 128}, o16);
+  auto delta = torch::empty({E, ht, wd, 2}, o32);
+  auto weight = torch::empty({E, ht, wd, 2}, o32);
+  torch::Tensor eta, upmask;
+  if (agg) { eta = torch::empty({n_src, ht, wd}, o32); upmask = torch::empty({n_src, 576, ht, wd}, o16); }
+  const size_t ws_bytes = dba_update_workspace_bytes(E, agg ? (int)n_src : 0, ht, wd);
+  auto ws = torch::empty({(int64_t)ws_bytes + 256}, torch::TensorOptions().dtype(torch::kUInt8).device(net.device()));
+  dba_update_args a;
+  memset(&a, 0, sizeof(a));
+  a.n_edges = E; a.ht = ht; a.wd = wd;
+  a.net = net.data_ptr(); a.net_dtype = dtype_code(net, "update_forward"); a.net_layout = net_channels_last ? 1 : 0;
+  a.inp = inp.data_ptr(); a.inp_dtype = dtype_code(inp, "update_forward");
+  a.corr = corr.data_ptr(); a.corr_dtype = dtype_code(corr, "update_forward");
+  a.flow = flow_c.defined() ? flow_c.data_ptr<float>() : nullptr;
+  a.seg = agg ? seg_c.data_ptr<int64_t>() : nullptr; a.n_src = agg ? (int)n_src : 0;
+  a.weights = &W;
+  a.net_out = net_out.data_ptr(); a.delta = delta.data_ptr<float>(); a.weight = weight.data_ptr<float>();
+  a.eta = agg ? eta.data_ptr<float>() : nullptr; a.upmask = agg ? upmask.data_ptr() : nullptr;
+  a.workspace = (void*)(((uintptr_t)ws.data_ptr() + 255) & ~(uintptr_t)255); a.workspace_bytes = ws_bytes; a.stream = cur_stream();
+  check_status(dba_update_forward(&a), "update_forward");
+  if (agg) return {net_out, delta, weight, eta, upmask};
+  return {net_out, delta, weight};
+}
+
+// extension: channels-last tensor-core convolution (building block of update_forward).  src0 [E,ht,wd,C0] f16 (+ src1 [E,ht,wd,C1]),
+// wpk f16 [k*k][N][Kpad], bias f32 [N] -> [E,ht,wd,N] f16
+torch::Tensor conv_nhwc(torch::Tensor src0, c10::optional<torch::Tensor> src1, torch::Tensor wpk, torch::Tensor bias, int64_t ksize, bool relu) {
+  CHECK_INPUT(src0); CHECK_INPUT(wpk); CHECK_INPUT(bias); CHECK_F32(bias);
+  TORCH_CHECK(src0.dim() == 4 && src0.scalar_type() == torch::kFloat16 && wpk.dim() == 3 && wpk.scalar_type() == torch::kFloat16, "src0 [E,ht,wd,C] f16, wpk [taps,N,K] f16");
+  c10::cuda::CUDAGuard guard(src0.device());
+  const int E = (int)src0.size(0), ht = (int)src0.size(1), wd = (int)src0.size(2), C0 = (int)src0.size(3), N = (int)wpk.size(1);
+  const void* s1 = nullptr; int C1 = 0;
+  torch::Tensor s1t;
+  if (src1.has_value() && src1->defined()) { s1t = *src1; CHECK_INPUT(s1t); TORCH_CHECK(s1t.scalar_type() == torch::kFloat16 && s1t.dim() == 4, "src1 [E,ht,wd,C] f16"); s1 = s1t.data_ptr(); C1 = (int)s1t.size(3); }
+  TORCH_CHECK(wpk.size(0) == ksize * ksize && wpk.size(2) == 64 * ((C0 + 63) / 64) + 64 * ((C1 + 63) / 64) && bias.numel() == N, "packed weight shape mismatch");
+  auto out = torch::empty({E, ht, wd, N}, src0.options());
+  check_status(dba_conv_nhwc(src0.data_ptr(), C0, C0, s1, C1, C1, wpk.data_ptr(), bias.data_ptr<float>(), out.data_ptr(), N, E, ht, wd, (int)ksize, N,
+                             relu ? 1 : 0, cur_stream()), "conv_nhwc");
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native droid_backends (drop-in for princeton-vl/DROID-SLAM src/droid.cpp)";
   // bundle adjustment kernels
@@ -262,5 +342,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("corr_index_backward", &corr_index_backward, "INDEX backward");
   m.def("corr_volume_pyramid", &corr_volume_pyramid, "all-pairs correlation + 4-level pyramid (tcgen05), B200 extension");
   m.def("reproject", &reproject, "fused pops.projective_transform(jacobian=False), B200 extension");
+  m.def("update_forward", &update_forward, "update operator (ConvGRU + heads + GraphAgg) on tcgen05, B200 extension");
+  m.def("conv_nhwc", &conv_nhwc, "channels-last 1x1/3x3 convolution on tcgen05, B200 extension");
   m.def("_b200_native", []() { return true; });
 }

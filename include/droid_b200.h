@@ -155,6 +155,54 @@ int dba_ba_p2p_signal(const dba_ba_args* a);   /* after dba_ba_build, before dba
  * bit2 = Cholesky hit a non-positive pivot in some iteration -> that iteration's dx = 0 like the reference). */
 int dba_ba_read_info(const dba_ba_args* a, int* n_depth_frames, int* device_status);
 
+/* ---- update operator (ConvGRU + heads + GraphAgg) on the tensor cores -----------------------------------
+ * replaces UpdateModule.forward (reference droid_slam/droid_net.py:111-143), ConvGRU.forward (droid_slam/modules/gru.py:19-32) and
+ * GraphAgg.forward (droid_net.py:59-75) -- in the reference a chain of 19 cuDNN convolutions + ~25 elementwise launches.
+ * Every convolution runs as an implicit GEMM (tcgen05 / TMEM / TMA, f16 operands, fp32 accumulation) on channels-last
+ * activations; gates, activations, the global-context sum and output layouts are fused into the epilogues.
+ *
+ * Packed weights (device memory, made once per checkpoint by the host side, droid_slam_b200/update.py:pack_update_weights):
+ *   w_* : f16 [taps][N][Kpad]  (tap = dy*k + dx, K = input channels in the reference's concatenation order, zero padded to a
+ *         multiple of 64), b_* : f32 [N]
+ *   w_corr0 [1][128][256]  corr_encoder.0 (196 in)        w_corr2 [9][128][128] corr_encoder.2
+ *   w_flow0 [1][128][256]  flow_encoder.0, K = (dy*7+dx)*4 + c (7x7 taps folded into K)     w_flow2 [9][64][128] flow_encoder.2
+ *   w_gate  [1][128][128]  gru.w          w_glo f32 [384][128] = gru.convz_glo | convr_glo | convq_glo, b_glo [384]
+ *   w_zr    [9][256][448]  gru.convz | gru.convr         w_q [9][128][448] gru.convq
+ *   w_stem  [9][384][128]  delta.0 | weight.0 | agg.conv1
+ *   w_heads [9][32][256]   rows 0-1 = delta.2 on K 0..127, rows 2-3 = weight.2 on K 128..255, rest 0;  b_heads [32]
+ *   w_agg2  [9][128][128]  agg.conv2      w_eta [9][32][128] row 0 = agg.eta.0, b_eta [32]      w_upmask [1][576][128] agg.upmask.0 */
+typedef struct {
+  const void *w_corr0, *w_corr2, *w_flow0, *w_flow2, *w_gate, *w_zr, *w_q, *w_stem, *w_heads, *w_agg2, *w_eta, *w_upmask;
+  const float *b_corr0, *b_corr2, *b_flow0, *b_flow2, *b_gate, *b_zr, *b_q, *b_stem, *b_heads, *b_agg2, *b_eta, *b_upmask;
+  const float *w_glo, *b_glo;
+} dba_update_weights;
+
+typedef struct {
+  int n_edges, ht, wd;
+  const void* net;  int net_dtype;  int net_layout;   /* hidden state [E,128,ht,wd] (layout 0, DBA_F16 / DBA_F32) or channels-last f16 [E,ht,wd,128] (layout 1) */
+  const void* inp;  int inp_dtype;                     /* context features [E,128,ht,wd] */
+  const void* corr; int corr_dtype;                    /* correlation features [E,196,ht,wd] */
+  const float* flow;                                   /* motion features [E,4,ht,wd] f32, or NULL (= zeros, MotionFilter's call) */
+  const int64_t* seg; int n_src;                       /* seg[e] = rank of edge e's source frame among the distinct sources (torch.unique
+                                                          inverse); n_src = number of distinct sources; n_src = 0: no aggregation outputs */
+  const dba_update_weights* weights;                   /* HOST struct of DEVICE pointers */
+  void* net_out;                                       /* new hidden state, channels-last f16 [E,ht,wd,128] */
+  float* delta;  float* weight;                        /* [E,ht,wd,2] f32: flow revision, confidence (sigmoid) */
+  float* eta;    void* upmask;                         /* [n_src,ht,wd] f32 (0.01 * softplus), [n_src,576,ht,wd] f16 */
+  void* workspace; size_t workspace_bytes;             /* dba_update_workspace_bytes(), 256-byte aligned */
+  dba_stream_t stream;
+} dba_update_args;
+
+size_t dba_update_workspace_bytes(int n_edges, int n_src, int ht, int wd);
+int dba_update_forward(const dba_update_args* a);
+
+/* the building block of dba_update_forward, exported: 1x1 / 3x3 'same' convolution of channels-last f16 activations on the tensor
+ * cores.  src0 (+ optional src1, concatenated along channels after src0) [n_images,ht,wd,stride] using channels [0,c); wpk f16
+ * [ksize*ksize][n_out][Kpad] with Kpad = 64*ceil(c0/64) + 64*ceil(c1/64), K contiguous; bias f32 [n_out]; out f16
+ * [n_images,ht,wd,out_stride] channels [0,n_out) written.  n_out in {32,64,...,256,384}. */
+int dba_conv_nhwc(const void* src0, int c0, int stride0, const void* src1, int c1, int stride1, const void* wpk, const float* bias,
+                  void* out, int out_stride, int n_images, int ht, int wd, int ksize, int n_out, int relu, dba_stream_t stream);
+
 /* ---- standalone damped SPD solve (the solver inside dba_ba_solve) ---------------------------------------
  * (H + diag(ep + lm*diag(H))) x = b with H [n,n] fp64 (full symmetric), b [n] fp64 -> x [n] fp32, on the device in
  * fp64; replaces SparseBlock::solve (reference src/droid_kernels.cu:1201-1222).  *fail_flag_device is set to 1 and x to 0
