@@ -60,7 +60,7 @@ __host__ inline Layout make_layout(int N, int E, int ht, int wd, int t0, int t1)
 
 // header words
 enum { HDR_STATUS = 0, HDR_M = 1, HDR_CHOL_FAIL = 2 };
-enum { ST_BAD_INDEX = 1, ST_ETA_ROWS = 2, ST_CHOL_FAIL = 4 };
+enum { ST_BAD_INDEX = 1, ST_ETA_ROWS = 2, ST_CHOL_FAIL = 4, ST_DEGREE = 8 };
 
 // ---------------------------------------------------------------------------------------------------------
 // prepare: kx = sorted unique(ii U [t0,t1)), frame2k, CSR of edges by source frame (stable in edge order)
@@ -436,7 +436,12 @@ __global__ void __launch_bounds__(kBuildThreads, 2) ba_build_kernel(
 // dense graphs, edge-sharded ranks).  Both keep 6x6 block pairs in registers over a whole pixel chunk, accumulate in fp32 like the
 // reference and flush once with fp64 atomics into the LOWER triangle of the reduced system.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kSchurMaxRows = 255;   // rows per frame (out-degree + 1); larger frames raise ST_BAD_INDEX
+// Q = 1/C of the eliminated depth block.  C <= 0 only for a pixel with eta = 0 and no weight on any edge; the reference divides
+// anyway (inf -> NaN system -> zero pose update and NaN depths at that pixel).  All Schur kernels and the back-substitution here
+// drop such a pixel instead (Q = 0, dz = 0): one rule on every path, documented in INTEGRATION.md.
+__device__ __forceinline__ float safe_rcp(float c) { return c > 0.f ? 1.0f / c : 0.f; }
+
+constexpr int kSchurMaxRows = 255;   // rows per frame (out-degree + 1); larger frames raise ST_DEGREE
 
 // Row list of a depth frame: (pose ix, Ei) first when ix is inside the window, then (pose jj[e], Eij[e]) for its out-edges in CSR
 // order whose target pose is inside the window.  Built by the whole CTA: thread a handles out-edge a, an order-preserving
@@ -464,7 +469,7 @@ __device__ __forceinline__ void build_row_list(const int64_t* __restrict__ jj, i
     int tot = self ? 1 : 0;
     for (int w = 0; w < kThreads / 32; w++) tot += s_wcount[w];
     *s_nrows = tot;
-    if (deg > kSchurMaxRows - 1) atomicOr(&hdr[HDR_STATUS], ST_BAD_INDEX);
+    if (deg > kSchurMaxRows - 1) atomicOr(&hdr[HDR_STATUS], ST_DEGREE);
   }
   __syncthreads();
 }
@@ -536,7 +541,7 @@ __global__ void __launch_bounds__(kSgThreads) ba_schur_gemm_kernel(
       // ---- stage: A tile scaled by Q, B tile raw; one warp per (row, component) line of 64 pixels, transposed into [px][row*6+c]
       for (int px = tid; px < kSgK; px += kSgThreads) {
         const bool okp = px < np;
-        const float q = okp ? 1.0f / __ldg(Cin + (size_t)m * HW + p0 + px) : 0.f;
+        const float q = okp ? safe_rcp(__ldg(Cin + (size_t)m * HW + p0 + px)) : 0.f;
         sQ[px] = q;
         sQw[px] = okp ? __ldg(win + (size_t)m * HW + p0 + px) : 0.f;
       }
@@ -671,8 +676,8 @@ __global__ void __launch_bounds__(kSgThreads, 2) ba_schur_small_kernel(
     const int np = min(kSgK, px_end - p0);
     const bool ok0 = lane < np, ok1 = lane + 32 < np;
     const size_t base = (size_t)m * HW + p0;
-    q0 = ok0 ? 1.0f / __ldg(Cin + base + lane) : 0.f;
-    q1 = ok1 ? 1.0f / __ldg(Cin + base + lane + 32) : 0.f;
+    q0 = ok0 ? safe_rcp(__ldg(Cin + base + lane)) : 0.f;
+    q1 = ok1 ? safe_rcp(__ldg(Cin + base + lane + 32)) : 0.f;
     w0 = ok0 ? __ldg(win + base + lane) : 0.f;
     w1 = ok1 ? __ldg(win + base + lane + 32) : 0.f;
 #pragma unroll
@@ -1179,7 +1184,7 @@ __global__ void __launch_bounds__(256) ba_backsub_kernel(
       dw += s;
     }
   }
-  const float q = 1.0f / __ldg(Cin + (size_t)m * HW + p);
+  const float q = safe_rcp(__ldg(Cin + (size_t)m * HW + p));
   const float dz = q * (__ldg(win + (size_t)m * HW + p) - dw);
   dz_out[(size_t)m * HW + p] = owned ? dz : 0.f;
   if (owned) disps[(size_t)ix * HW + p] += dz;       // K8 (:942-955)

@@ -11,6 +11,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <vector>
+#include <cuda_runtime_api.h>
 #include <cstring>
 #include "../../../include/droid_b200.h"
 
@@ -34,6 +35,16 @@ static int dtype_code(const torch::Tensor& t, const char* what) {
     default: TORCH_CHECK(false, what, ": unsupported dtype ", t.scalar_type());
   }
   return -1;
+}
+
+// sticky device status word of a ba call (include/droid_b200.h: dba_ba_read_info)
+static void check_ba_status(int st, bool after_solve) {
+  TORCH_CHECK(!(st & 1), "droid_backends.ba: ii/jj hold frame indices outside [0, n_frames) (the reference reads out of bounds here)");
+  TORCH_CHECK(!(st & 8), "droid_backends.ba: a source frame has more than 254 out-edges; the Schur complement kernels hold at most 255 rows per depth frame");
+  TORCH_CHECK(!(st & 2), "droid_backends.ba: eta row count does not match the number of depth frames");
+  if (after_solve && (st & 4))
+    TORCH_WARN("droid_backends.ba: the damped pose system was not positive definite in at least one Gauss-Newton iteration; that iteration's "
+               "update is zero (the reference does the same silently, src/droid_kernels.cu:1216-1219)");
 }
 
 std::vector<torch::Tensor> ba(torch::Tensor poses, torch::Tensor disps, torch::Tensor intrinsics, torch::Tensor disps_sens,
@@ -73,6 +84,7 @@ std::vector<torch::Tensor> ba(torch::Tensor poses, torch::Tensor disps, torch::T
   auto dx = torch::empty({P, 6}, poses.options());
 
   dba_ba_args a;
+  memset(&a, 0, sizeof(a));
   a.poses = poses.data_ptr<float>(); a.disps = disps.data_ptr<float>(); a.intrinsics = intrinsics.data_ptr<float>();
   a.disps_sens = disps_sens.data_ptr<float>(); a.targets = targets.data_ptr<float>(); a.weights = weights.data_ptr<float>();
   a.eta = motion_only ? nullptr : eta_c.data_ptr<float>(); a.eta_rows = eta_rows;
@@ -82,20 +94,37 @@ std::vector<torch::Tensor> ba(torch::Tensor poses, torch::Tensor disps, torch::T
   a.dx_out = dx.data_ptr<float>(); a.dz_out = nullptr;
   a.workspace = ws.data_ptr(); a.workspace_bytes = ws_bytes; a.stream = cur_stream();
   a.own_lo = 0; a.own_hi = n_frames; a.eta_by_frame = 0;
-  a.p2p_world = 0; a.p2p_rank = 0; a.p2p_epoch = 0; for (int k = 0; k < 8; k++) a.p2p_system[k] = nullptr;
 
+  // The graph bookkeeping runs first and its result is read back (one stream synchronisation; the reference's ba synchronises a
+  // dozen times per call): the number of depth frames M sizes dz, eta must have 1 or M rows (the reference raises a broadcast
+  // error otherwise, src/droid_kernels.cu:1407), and out-of-range indices are reported instead of being dropped.  While the stream
+  // is being captured into a CUDA graph no synchronisation is possible: dz is sized from eta and the checks are skipped (the
+  // caller validated the same tensors eagerly).
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing((cudaStream_t)a.stream, &cap);
+  const bool capturing = cap != cudaStreamCaptureStatusNone;
   torch::Tensor dz;
+  int M = eta_rows;
+  if (!capturing) {
+    check_status(dba_ba_prepare(&a), "ba");
+    int st = 0;
+    check_status(dba_ba_read_info(&a, &M, &st), "ba");
+    check_ba_status(st, /*after_solve=*/false);
+    TORCH_CHECK(motion_only || eta_rows == 1 || eta_rows == M, "ba: eta has ", eta_rows, " rows but the graph has ", M,
+                " depth frames (unique(ii U [t0,t1)))");
+  } else {
+    TORCH_CHECK(motion_only || eta_rows > 1, "ba: a broadcast (1-row) eta needs the depth-frame count from the device and cannot be used during CUDA graph capture");
+  }
   if (!motion_only) {
-    int M = eta_rows;
-    if (eta_rows == 1) {   // broadcast eta: the number of depth frames has to come from the device (one sync)
-      check_status(dba_ba_prepare(&a), "ba");
-      int st = 0;
-      check_status(dba_ba_read_info(&a, &M, &st), "ba");
-    }
     dz = torch::empty({M, HW}, poses.options());
     a.dz_out = dz.data_ptr<float>();
   }
   check_status(dba_ba(&a, iterations), "ba");
+  if (!capturing) {
+    int st = 0, m2 = 0;
+    check_status(dba_ba_read_info(&a, &m2, &st), "ba");
+    check_ba_status(st, /*after_solve=*/true);
+  }
   return {dx, dz};
 }
 

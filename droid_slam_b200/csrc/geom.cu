@@ -16,14 +16,14 @@ __global__ void __launch_bounds__(256) projmap_kernel(const float* __restrict__ 
                                                       const float* __restrict__ intr, const int64_t* __restrict__ ii,
                                                       const int64_t* __restrict__ jj, float* __restrict__ coords,
                                                       float* __restrict__ valid, int ht, int wd) {
-  const int e = blockIdx.y;
+  const int e = blockIdx.x;   // edges / frames on grid.x (2^31-1 blocks), pixel chunks on grid.y
   __shared__ float T[7];
   const int ix = (int)ii[e], jx = (int)jj[e];
   if (threadIdx.x == 0) edge_transform(poses, ix, jx, /*stereo_quirk=*/false, T, T + 3);   // no stereo branch (:475-490)
   __syncthreads();
   const Intr K = load_intr(intr);
   const int hw = ht * wd;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y * blockDim.x + threadIdx.x;
   if (k >= hw) return;
   const int i = k / wd, j = k - i * wd;
   const float u = (float)j, v = (float)i;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) depth_filter_kernel(const float* __restri
                                                            const float* __restrict__ intr, const int64_t* __restrict__ inds,
                                                            const float* __restrict__ thresh, float* __restrict__ counter,
                                                            int num, int ht, int wd) {
-  const int b = blockIdx.y;
+  const int b = blockIdx.x;   // edges / frames on grid.x (2^31-1 blocks), pixel chunks on grid.y
   __shared__ float T[6][7];
   __shared__ int J[6];
   const int ix = (int)inds[b];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) depth_filter_kernel(const float* __restri
   __syncthreads();
   const Intr K = load_intr(intr);
   const int hw = ht * wd;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y * blockDim.x + threadIdx.x;
   if (k >= hw) return;
   const int i = k / wd, j = k - i * wd;
   const float ui = (float)j, vi = (float)i;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) depth_filter_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) iproj_kernel(const float* __restrict__ poses, const float* __restrict__ disps,
                                                     const float* __restrict__ intr, float* __restrict__ points, int ht, int wd) {
-  const int n = blockIdx.y;
+  const int n = blockIdx.x;   // edges / frames on grid.x (2^31-1 blocks), pixel chunks on grid.y
   const Intr K = load_intr(intr);
   float t[3], q[4];
 #pragma unroll
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) iproj_kernel(const float* __restrict__ po
 #pragma unroll
   for (int k = 0; k < 4; k++) q[k] = __ldg(poses + 7 * (size_t)n + 3 + k);
   const int hw = ht * wd;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y * blockDim.x + threadIdx.x;
   if (k >= hw) return;
   const int i = k / wd, j = k - i * wd;
   float Xi[4] = {((float)j - K.cx) / K.fx, ((float)i - K.cy) / K.fy, 1.f, __ldg(disps + (size_t)n * hw + k)}, Xj[4];
@@ -161,14 +161,14 @@ __global__ void __launch_bounds__(256) reproject_kernel(const float* __restrict_
                                                         const float* __restrict__ intr, const int64_t* __restrict__ ii,
                                                         const int64_t* __restrict__ jj, float* __restrict__ coords,
                                                         float* __restrict__ valid, int ht, int wd) {
-  const int e = blockIdx.y;
+  const int e = blockIdx.x;   // edges / frames on grid.x (2^31-1 blocks), pixel chunks on grid.y
   __shared__ float T[7];
   const int ix = (int)ii[e], jx = (int)jj[e];
   if (threadIdx.x == 0) edge_transform(poses, ix, jx, /*stereo_quirk=*/true, T, T + 3);
   __syncthreads();
   const Intr Ki = load_intr(intr + 4 * (size_t)ix), Kj = load_intr(intr + 4 * (size_t)jx);
   const int hw = ht * wd;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y * blockDim.x + threadIdx.x;
   if (k >= hw) return;
   const int i = k / wd, j = k - i * wd;
   float Xi[4] = {((float)j - Ki.cx) / Ki.fx, ((float)i - Ki.cy) / Ki.fy, 1.f, __ldg(disps + (size_t)ix * hw + k)}, Xj[4];
@@ -190,8 +190,8 @@ extern "C" int dba_reproject(const float* poses, const float* disps, const float
   DBA_CHECK_ARG(n_edges >= 0 && ht >= 0 && wd >= 0, "negative extent");
   if (n_edges == 0 || ht * wd == 0) return DBA_OK;
   DBA_CHECK_ARG(poses && disps && intrinsics_per_frame && ii && jj && coords && valid, "null pointer");
-  DBA_CHECK_ARG(n_edges <= 65535, "more than 65535 edges in one reproject call");
-  dim3 grid((ht * wd + 255) / 256, n_edges);
+  DBA_CHECK_ARG((ht * wd + 255) / 256 <= 65535, "image too large");
+  dim3 grid(n_edges, (ht * wd + 255) / 256);
   reproject_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics_per_frame, ii, jj, coords, valid, ht, wd);
   DBA_CHECK_LAUNCH("reproject");
   return DBA_OK;
@@ -202,8 +202,8 @@ extern "C" int dba_projmap(const float* poses, const float* disps, const float* 
   DBA_CHECK_ARG(n_edges >= 0 && ht >= 0 && wd >= 0, "negative extent");
   if (n_edges == 0 || ht * wd == 0) return DBA_OK;
   DBA_CHECK_ARG(poses && disps && intrinsics && ii && jj && coords && valid, "null pointer");
-  DBA_CHECK_ARG(n_edges <= 65535, "more than 65535 edges in one projmap call");
-  dim3 grid((ht * wd + 255) / 256, n_edges);
+  DBA_CHECK_ARG((ht * wd + 255) / 256 <= 65535, "image too large");
+  dim3 grid(n_edges, (ht * wd + 255) / 256);
   projmap_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics, ii, jj, coords, valid, ht, wd);
   DBA_CHECK_LAUNCH("projmap");
   return DBA_OK;
@@ -224,8 +224,8 @@ extern "C" int dba_depth_filter(const float* poses, const float* disps, const fl
   DBA_CHECK_ARG(num >= 0 && n_disps >= 0 && ht >= 0 && wd >= 0, "negative extent");
   if (num == 0 || ht * wd == 0) return DBA_OK;
   DBA_CHECK_ARG(poses && disps && intrinsics && ix && thresh && counter, "null pointer");
-  DBA_CHECK_ARG(num <= 65535, "more than 65535 frames in one depth_filter call");
-  dim3 grid((ht * wd + 255) / 256, num);
+  DBA_CHECK_ARG((ht * wd + 255) / 256 <= 65535, "image too large");
+  dim3 grid(num, (ht * wd + 255) / 256);
   depth_filter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics, ix, thresh, counter, n_disps, ht, wd);
   DBA_CHECK_LAUNCH("depth_filter");
   return DBA_OK;
@@ -236,8 +236,8 @@ extern "C" int dba_iproj(const float* poses, const float* disps, const float* in
   DBA_CHECK_ARG(n >= 0 && ht >= 0 && wd >= 0, "negative extent");
   if (n == 0 || ht * wd == 0) return DBA_OK;
   DBA_CHECK_ARG(poses && disps && intrinsics && points, "null pointer");
-  DBA_CHECK_ARG(n <= 65535, "more than 65535 frames in one iproj call");
-  dim3 grid((ht * wd + 255) / 256, n);
+  DBA_CHECK_ARG((ht * wd + 255) / 256 <= 65535, "image too large");
+  dim3 grid(n, (ht * wd + 255) / 256);
   iproj_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(poses, disps, intrinsics, points, ht, wd);
   DBA_CHECK_LAUNCH("iproj");
   return DBA_OK;

@@ -152,7 +152,8 @@ int dba_ba(const dba_ba_args* a, int iterations);
 int dba_ba_p2p_signal(const dba_ba_args* a);   /* after dba_ba_build, before dba_ba_solve, when p2p_world > 1 */
 /* synchronises `stream` and reads back M = number of depth frames found by the last dba_ba_prepare on this
  * workspace and the sticky device status word (0 = ok, bit0 = index out of range, bit1 = eta rows != M,
- * bit2 = Cholesky hit a non-positive pivot in some iteration -> that iteration's dx = 0 like the reference). */
+ * bit2 = Cholesky hit a non-positive pivot in some iteration -> that iteration's dx = 0 like the reference,
+ * bit3 = a source frame has more than 254 out-edges: its Schur complement would be truncated, the result is not usable). */
 int dba_ba_read_info(const dba_ba_args* a, int* n_depth_frames, int* device_status);
 
 /* ---- update operator (ConvGRU + heads + GraphAgg) on the tensor cores -----------------------------------
