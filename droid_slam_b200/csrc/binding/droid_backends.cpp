@@ -370,6 +370,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("corr_index_forward", &corr_index_forward, "INDEX forward");
   m.def("corr_index_backward", &corr_index_backward, "INDEX backward");
   m.def("corr_volume_pyramid", &corr_volume_pyramid, "all-pairs correlation + 4-level pyramid (tcgen05), B200 extension");
+  m.def("corr_volume_supported", [](int dim, int ht, int wd) { return dba_corr_volume_supported(dim, ht, wd, DBA_F16) != 0; }, "does corr_volume_pyramid have a kernel for f16 [.,dim,ht,wd] feature maps");
   m.def("reproject", &reproject, "fused pops.projective_transform(jacobian=False), B200 extension");
   m.def("update_forward", &update_forward, "update operator (ConvGRU + heads + GraphAgg) on tcgen05, B200 extension");
   m.def("conv_nhwc", &conv_nhwc, "channels-last 1x1/3x3 convolution on tcgen05, B200 extension");

@@ -248,6 +248,10 @@ static int make_fmap_tensor_map(CUtensorMap* map, const void* base, int n_frames
 }  // namespace dba
 using namespace dba;
 
+extern "C" int dba_corr_volume_supported(int channels, int ht, int wd, int dtype) {
+  return (dtype == DBA_F16 && channels == 128 && wd == 64 && ht > 0 && ht % 8 == 0) ? 1 : 0;
+}
+
 extern "C" int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj, void* out0, void* out1,
                                        void* out2, void* out3, int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd,
                                        int dtype, dba_stream_t stream) {

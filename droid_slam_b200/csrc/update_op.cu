@@ -23,6 +23,7 @@
 #include "tcgen05.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace dba {
 
@@ -523,7 +524,7 @@ static int g_num_sms = 0;
 // one convolution launch.  src0 (+ optional src1) = channels-last sources concatenated along K; wpk = packed weights
 // [KS*KS][n_ntiles*N][Kpad] with Kpad = 64 * (kblocks(src0) + kblocks(src1)).
 template <int EPI>
-static int launch_conv(ConvParams p, ConvSrc s0, ConvSrc s1, const void* wpk, cudaStream_t st) {
+static int launch_conv(ConvParams p, ConvSrc s0, ConvSrc s1, const void* wpk, cudaStream_t st, int* slots_out = nullptr) {
   if (!g_num_sms) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceProp prop; DBA_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
@@ -531,7 +532,13 @@ static int launch_conv(ConvParams p, ConvSrc s0, ConvSrc s1, const void* wpk, cu
   }
   p.TW = (p.WD % 64 == 0) ? 64 : 32;
   p.RM = 128 / p.TW;
+  // M tiles per CTA tile: every weight stage is shared by MT tiles (and every halo row by 3 taps), so larger is better for the
+  // L2 -> SM traffic per MAC; bounded by TMEM (MT * N <= 512 columns) and by the image height
   p.MT = (p.N <= 256 && p.HT >= 2 * p.RM) ? 2 : 1;
+  static const int ov_mt = getenv("DBA_CONV_MT") ? atoi(getenv("DBA_CONV_MT")) : 0;          // experiment switches (tools/conv_bench.py)
+  static const int ov_as = getenv("DBA_CONV_ASTAGES") ? atoi(getenv("DBA_CONV_ASTAGES")) : 0;
+  static const int ov_bs = getenv("DBA_CONV_BSTAGES") ? atoi(getenv("DBA_CONV_BSTAGES")) : 0;
+  if (ov_mt > 0 && ov_mt * p.N <= 512 && ov_mt <= 4) p.MT = ov_mt;
   p.tiles_x = (p.WD + p.TW - 1) / p.TW;
   p.tiles_y = (p.HT + p.MT * p.RM - 1) / (p.MT * p.RM);
   p.nk0 = (s0.C + 63) / 64;
@@ -541,11 +548,18 @@ static int launch_conv(ConvParams p, ConvSrc s0, ConvSrc s1, const void* wpk, cu
   const int box_rows = p.MT * p.RM + p.KS - 1;
   p.a_bytes = box_rows * p.TW * 128;
   p.b_bytes = p.N * 128;
+  // shared memory: at least 2 halo stages and 3 weight stages; what is left goes to more halo stages (up to 4: with narrow N the
+  // MMAs of a stage are short and the TMA latency of the next halo tile is what the pipeline has to cover), then weight stages
+  const int budget = 227 * 1024 - 2048;
   p.a_stages = 2;
-  const int budget = 227 * 1024 - 2048 - p.a_stages * p.a_bytes;
-  p.b_stages = budget / p.b_bytes;
-  if (p.b_stages > 6) p.b_stages = 6;
+  while (p.a_stages < 4 && (p.a_stages + 1) * p.a_bytes + 4 * p.b_bytes <= budget) p.a_stages++;
+  if (ov_as > 0 && ov_as <= 4) p.a_stages = ov_as;
+  p.b_stages = (budget - p.a_stages * p.a_bytes) / p.b_bytes;
+  if (p.b_stages > 8) p.b_stages = 8;
+  if (ov_bs > 0 && ov_bs <= 8 && p.a_stages * p.a_bytes + ov_bs * p.b_bytes <= budget) p.b_stages = ov_bs;
   if (p.b_stages < 2) { set_error("update operator: tile does not fit shared memory"); return DBA_ERR_INVALID; }
+  p.slots = p.tiles_x * p.tiles_y * p.MT * 4;
+  if (slots_out) *slots_out = p.slots;
   const int smem = p.a_stages * p.a_bytes + p.b_stages * p.b_bytes + 1024 + 256;
   CUtensorMap tA0, tA1, tW;
   int rc = make_act_map(&tA0, s0.base, s0.C, s0.stride, p.WD, p.HT, p.E, p.TW, box_rows); if (rc) return rc;
@@ -676,12 +690,9 @@ extern "C" int dba_update_forward(const dba_update_args* a) {
   { ConvParams p = base; p.KS = 3; p.N = 64; p.bias = W->b_flow2; p.relu = 1; p.out = X + 256; p.out_stride = 320;
     rc = launch_conv<EPI_STORE>(p, ConvSrc{F1, 128, 128}, none, W->w_flow2, st); if (rc) return rc; }
   // ---- ConvGRU (gru.py:19-32): global context
-  int slots;
+  int slots = 0;
   { ConvParams p = base; p.KS = 1; p.N = 128; p.bias = W->b_gate; p.h = H; p.h_stride = 128; p.partial = partial;
-    const int tw = (wd % 64 == 0) ? 64 : 32, rm = 128 / tw, mt = (ht >= 2 * rm) ? 2 : 1;
-    slots = ((wd + tw - 1) / tw) * ((ht + mt * rm - 1) / (mt * rm)) * mt * 4;
-    p.slots = slots;
-    rc = launch_conv<EPI_GATE>(p, ConvSrc{H, 128, 128}, none, W->w_gate, st); if (rc) return rc; }
+    rc = launch_conv<EPI_GATE>(p, ConvSrc{H, 128, 128}, none, W->w_gate, st, &slots); if (rc) return rc; }
   glo_kernel<<<E, 384, 0, st>>>(partial, slots, 1.f / (float)HW, W->w_glo, W->b_glo, glo);
   DBA_CHECK_LAUNCH("glo_kernel");
   // z, r = sigmoid(conv3x3(h | x) + glo): one 256-output convolution; epilogue writes z and r*h
@@ -722,7 +733,7 @@ extern "C" int dba_conv_nhwc(const void* src0, int c0, int stride0, const void* 
   DBA_CHECK_ARG(n_images >= 0 && ht > 0 && wd > 0, "bad extents");
   DBA_CHECK_ARG(ksize == 1 || ksize == 3, "kernel size must be 1 or 3");
   DBA_CHECK_ARG(n_out >= 32 && n_out <= 384 && (n_out <= 256 ? n_out % 32 == 0 : n_out == 384), "n_out must be 32..256 (multiple of 32) or 384");
-  DBA_CHECK_ARG(c0 > 0 && c0 % 8 == 0 && stride0 % 8 == 0 && (!src1 || (c1 > 0 && c1 % 8 == 0 && stride1 % 8 == 0)), "channel counts / strides must be multiples of 8");
+  DBA_CHECK_ARG(c0 > 0 && stride0 % 8 == 0 && stride0 >= c0 && (!src1 || (c1 > 0 && stride1 % 8 == 0 && stride1 >= c1)), "row pitches must be multiples of 8 elements and hold the channels");
   DBA_CHECK_ARG(!src1 || c0 % 64 == 0, "with two sources the first must hold a multiple of 64 channels");
   DBA_CHECK_ARG(out_stride % 8 == 0 && out_stride >= n_out, "bad output stride");
   if (n_images == 0) return DBA_OK;

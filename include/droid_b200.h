@@ -56,6 +56,8 @@ int dba_corr_index_backward(const float* coords, const void* corr_grad, void* vo
  * ii,jj [E] int64 frame indices into fmap1 / fmap2;  out_l [E,ht,wd,ht/2^l,wd/2^l] f16 for l = 0..3, fully overwritten.
  * One tcgen05/TMEM/TMA kernel writes all four levels in a single pass over the accumulator.
  * Implemented for wd = 64, ht % 8 == 0 (DBA_ERR_INVALID otherwise). */
+/* 1 when dba_corr_volume_pyramid has a kernel for this shape / dtype (f16, 128 channels, wd = 64, ht % 8 == 0), else 0 */
+int dba_corr_volume_supported(int channels, int ht, int wd, int dtype);
 int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj,
                             void* out0, void* out1, void* out2, void* out3,
                             int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd, int dtype, dba_stream_t stream);

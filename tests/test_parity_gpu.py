@@ -292,29 +292,32 @@ def test_corr_volume_pyramid_tcgen05_matches_reference_formula(backends):
         corr = torch.nn.functional.avg_pool2d(corr, 2, stride=2)
 
 
-def test_corrblock_mirror_matches_oracle_lookup():
-    """droid_slam_b200.modules.CorrBlock / AltCorrBlock (the host-side mirror of reference modules/corr.py) end to end:
-    tensor-core volume build + lookup vs the oracle's CorrBlock restatement, and CorrBlock == AltCorrBlock"""
-    from droid_slam_b200.modules import AltCorrBlock, CorrBlock
+def test_tensor_core_volume_plus_lookup_matches_oracle_corrblock(backends):
+    """CorrBlock end to end the way the reference's class runs it on this module (constructor through the corr-volume hook,
+    droid_slam_b200/modules.py; lookups through corr_index_forward / altcorr_forward) vs the oracle's CorrBlock restatement, and
+    CorrBlock == AltCorrBlock"""
     g = torch.Generator().manual_seed(41)
     N, C, ht, wd = 4, 128, 16, 64
     fmaps = torch.randn(N, C, ht, wd, generator=g).half()
     ii = torch.tensor([0, 1, 2, 3, 0]); jj = torch.tensor([1, 2, 3, 0, 2])
     coords = torch.stack([torch.rand(1, 5, ht, wd, generator=g) * (wd + 4) - 2, torch.rand(1, 5, ht, wd, generator=g) * (ht + 4) - 2], dim=-1)
     f = fmaps.to(dev)
-    blk = CorrBlock(f[None, ii.to(dev)], f[None, jj.to(dev)])
-    got = blk(coords.to(dev))
+    pyr = backends.corr_volume_pyramid(f, f, ii.to(dev), jj.to(dev))
+    c = coords.permute(0, 1, 4, 2, 3).contiguous().view(5, 2, ht, wd).to(dev)
+    got = torch.cat([backends.corr_index_forward(pyr[l], (c / 2 ** l).contiguous(), 3)[0].view(1, 5, -1, ht, wd) for l in range(4)], dim=2)
     ref = oracle.corr_block_lookup(oracle.corr_pyramid(fmaps[None, ii].float(), fmaps[None, jj].float(), 4), coords, 3)
     assert got.shape == ref.shape == (1, 5, 196, ht, wd)
     assert float((got.float().cpu() - ref).abs().max()) < 0.1 and rel_err(got.float(), ref, floor=float(ref.abs().max())) < 5e-3
-    alt = AltCorrBlock(f[None])(coords.to(dev), ii.to(dev), jj.to(dev))
+    lv = []
+    fl = f
+    c5 = coords.permute(0, 1, 4, 2, 3).contiguous().to(dev)
+    for l in range(4):
+        o, = backends.altcorr_forward(f[None].contiguous(), fl[None].contiguous(), (c5 / 2 ** l).contiguous(), ii.to(dev), jj.to(dev), 3)
+        lv.append(o.flatten(2, 3))
+        fl = torch.nn.functional.avg_pool2d(fl, 2, stride=2)
+    alt = torch.stack(lv, dim=2).flatten(2, 3)
     assert alt.shape == got.shape
     assert rel_err(alt.float(), got.float(), floor=float(ref.abs().max())) < 1e-2      # two fp16 pipelines with different rounding points
-    # cat / __getitem__ helpers
-    blk2 = CorrBlock(f[None, ii[:2].to(dev)], f[None, jj[:2].to(dev)]).cat(CorrBlock(f[None, ii[2:].to(dev)], f[None, jj[2:].to(dev)]))
-    assert torch.equal(blk2(coords.to(dev)), got)
-    sub = blk2[torch.tensor([True, False, True, False, True], device=dev)]
-    assert sub.corr_pyramid[0].shape[0] == 3
 
 
 def test_fused_reproject_matches_projective_transform_restatement(backends):
