@@ -38,6 +38,7 @@ struct ConvParams {
   int KS;                           // kernel size 1 or 3
   int nk0, nk1;                     // 64-channel K blocks taken from source 0 / source 1
   int N;                            // accumulator columns per M tile
+  int w_rows;                       // rows per tap of the packed weight tensor (0: n_ntiles * N); larger when only the first N rows are used
   int boxn;                         // weight rows per TMA box
   int a_stages, b_stages, a_bytes, b_bytes;
   int nbuf;                         // TMEM accumulator buffers (2 when MT * N <= 256)
@@ -362,56 +363,74 @@ __global__ void __launch_bounds__(kUpThreads, 1) conv_tc_kernel(const __grid_con
 // small SIMT kernels around the tensor-core convolutions
 // ---------------------------------------------------------------------------------------------------------------------------
 
-// [E][C][HW] (f16 or f32) -> channels-last f16 dst[(e*HW + p) * dst_stride + c]; 64 x 64 tiles through shared memory so both sides
-// move 128-byte rows
+// [E][C][HW] (f16 or f32) -> channels-last f16 dst[(e*HW + p) * dst_stride + c] for c < cwrite (channels C..cwrite-1 are zeros).
+// 64 channels x 64 pixels per CTA; a thread loads a 2 x 2 (channel pair x pixel pair) patch, transposes it in registers and parks
+// the two channel-pair words in shared memory, so that both the global loads (pixel pairs of one channel row) and the global stores
+// (channel pairs of one pixel) are 4-byte lanes of 128-byte rows.
+template <typename T> struct Load2;
+template <> struct Load2<__half> {
+  static __device__ __forceinline__ float2 ld(const __half* p, bool ok0, bool ok1, bool aligned) {
+    if (ok1 && aligned) return __half22float2(*reinterpret_cast<const __half2*>(p));
+    return make_float2(ok0 ? __half2float(p[0]) : 0.f, ok1 ? __half2float(p[1]) : 0.f);
+  }
+};
+template <> struct Load2<float> {
+  static __device__ __forceinline__ float2 ld(const float* p, bool ok0, bool ok1, bool aligned) {
+    if (ok1 && aligned) return *reinterpret_cast<const float2*>(p);
+    return make_float2(ok0 ? p[0] : 0.f, ok1 ? p[1] : 0.f);
+  }
+};
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const T* __restrict__ src, __half* __restrict__ dst, int C, int HW, int dst_stride, int cwrite) {
-  __shared__ __half tile[64][66];
+  __shared__ uint32_t tile[64][33];                         // [pixel][channel pair]
   const int e = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 31, tyy = threadIdx.x >> 5;
-  for (int r = tyy; r < 64; r += 8) {
-    const int c = c0 + r;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool even = (HW & 1) == 0;                           // pixel pairs are 4 / 8-byte aligned when HW is even
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const int pp = p0 + tx + 32 * k;
-      float v = 0.f;
-      if (c < C && pp < HW) v = (float)src[((size_t)e * C + c) * HW + pp];
-      tile[r][tx + 32 * k] = __float2half_rn(v);
-    }
+  for (int k = 0; k < 4; k++) {
+    const int cp = w + 8 * k;                                // channel pair 0..31
+    const int c = c0 + 2 * cp, pp = p0 + 2 * lane;
+    float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+    if (c < C && pp < HW) a = Load2<T>::ld(src + ((size_t)e * C + c) * HW + pp, true, pp + 1 < HW, even);
+    if (c + 1 < C && pp < HW) b = Load2<T>::ld(src + ((size_t)e * C + c + 1) * HW + pp, true, pp + 1 < HW, even);
+    tile[2 * lane][cp] = pack2(a.x, b.x);
+    tile[2 * lane + 1][cp] = pack2(a.y, b.y);
   }
   __syncthreads();
-  for (int r = tyy; r < 64; r += 8) {
-    const int pp = p0 + r;
-    if (pp >= HW) continue;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const int c = c0 + tx + 32 * k;
-      if (c < cwrite) dst[((size_t)e * HW + pp) * dst_stride + c] = tile[tx + 32 * k][r];     // channels C..cwrite-1 are zeros
-    }
+  for (int k = 0; k < 8; k++) {
+    const int px = w + 8 * k, pp = p0 + px;
+    const int c = c0 + 2 * lane;
+    if (pp < HW && c < cwrite) *reinterpret_cast<uint32_t*>(dst + ((size_t)e * HW + pp) * dst_stride + c) = tile[px][lane];   // cwrite and strides are even
   }
 }
 
-// 7x7 / 4-channel flow encoder input as one 196-wide K: dst[(e*HW + p) * 200 + (dy*7+dx)*4 + c] = flow[e][c][y+dy-3][x+dx-3] (0 outside)
-__global__ void __launch_bounds__(256) flow_im2col_kernel(const float* __restrict__ flow, __half* __restrict__ dst, int HT, int WD, size_t total) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;     // (e, p, slot) with slot in 0..49 (49 = the 4 zero padding channels)
-  if (i >= total) return;
-  const int slot = (int)(i % 50);
-  const size_t ep = i / 50;
+// 7x7 / 4-channel flow encoder input as one 196-wide K: dst[(e*HW + p) * 200 + (dy*7+dx)*4 + c] = flow[e][c][y+dy-3][x+dx-3] (0 outside;
+// slot 49 = the 4 zero padding channels).  CTA = 64 pixels of one image row: the 4 x 7 x 70 halo goes through shared memory
+// (coalesced row loads), the 64 x 400-byte output rows leave as consecutive 8-byte lanes.
+__global__ void __launch_bounds__(256) flow_im2col_kernel(const float* __restrict__ flow, __half* __restrict__ dst, int HT, int WD) {
+  __shared__ float halo[4][7][72];
+  const int e = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 64;
   const int HW = HT * WD;
-  const int pp = (int)(ep % HW);
-  const size_t e = ep / HW;
-  const int y = pp / WD, x = pp - y * WD;
-  float v[4] = {0.f, 0.f, 0.f, 0.f};
-  if (slot < 49 && flow) {
-    const int dy = slot / 7, dx = slot - dy * 7;
-    const int yy = y + dy - 3, xx = x + dx - 3;
-    if (yy >= 0 && yy < HT && xx >= 0 && xx < WD) {
-#pragma unroll
-      for (int c = 0; c < 4; c++) v[c] = __ldg(flow + (e * 4 + c) * HW + (size_t)yy * WD + xx);
-    }
+  for (int i = threadIdx.x; i < 4 * 7 * 70; i += 256) {
+    const int c = i / 490, r = (i - c * 490) / 70, col = i - c * 490 - r * 70;
+    const int yy = y + r - 3, xx = x0 + col - 3;
+    float v = 0.f;
+    if (flow && yy >= 0 && yy < HT && xx >= 0 && xx < WD) v = __ldg(flow + ((size_t)e * 4 + c) * HW + (size_t)yy * WD + xx);
+    halo[c][r][col] = v;
   }
-  uint2 o = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
-  *reinterpret_cast<uint2*>(dst + ep * 200 + slot * 4) = o;
+  __syncthreads();
+  const int npx = min(64, WD - x0);
+  __half* out = dst + ((size_t)e * HW + (size_t)y * WD + x0) * 200;
+  for (int i = threadIdx.x; i < npx * 50; i += 256) {
+    const int px = i / 50, slot = i - px * 50;
+    uint2 o = make_uint2(0u, 0u);
+    if (slot < 49) {
+      const int dy = slot / 7, dx = slot - dy * 7;
+      o = make_uint2(pack2(halo[0][dy][px + dx], halo[1][dy][px + dx]), pack2(halo[2][dy][px + dx], halo[3][dy][px + dx]));
+    }
+    *reinterpret_cast<uint2*>(out + (size_t)i * 4) = o;
+  }
 }
 
 // global context (gru.py:25-30): g = mean over pixels of sigmoid(w(h)) * h (from the EPI_GATE partial sums), then the three 1x1
@@ -535,6 +554,9 @@ static int launch_conv(ConvParams p, ConvSrc s0, ConvSrc s1, const void* wpk, cu
   // M tiles per CTA tile: every weight stage is shared by MT tiles (and every halo row by 3 taps), so larger is better for the
   // L2 -> SM traffic per MAC; bounded by TMEM (MT * N <= 512 columns) and by the image height
   p.MT = (p.N <= 256 && p.HT >= 2 * p.RM) ? 2 : 1;
+  // N <= 128 with a long K loop (the q convolution): 4 tiles per weight stage beat the overlapped epilogue of 2 (measured:
+  // profiles/r2_conv_pipeline_experiments.txt); short K loops keep the double-buffered accumulators
+  if (p.N <= 128 && p.HT >= 4 * p.RM && (s0.C + 63) / 64 + (s1.base ? (s1.C + 63) / 64 : 0) >= 4 && p.KS == 3) p.MT = 4;
   static const int ov_mt = getenv("DBA_CONV_MT") ? atoi(getenv("DBA_CONV_MT")) : 0;          // experiment switches (tools/conv_bench.py)
   static const int ov_as = getenv("DBA_CONV_ASTAGES") ? atoi(getenv("DBA_CONV_ASTAGES")) : 0;
   static const int ov_bs = getenv("DBA_CONV_BSTAGES") ? atoi(getenv("DBA_CONV_BSTAGES")) : 0;
@@ -565,7 +587,7 @@ static int launch_conv(ConvParams p, ConvSrc s0, ConvSrc s1, const void* wpk, cu
   int rc = make_act_map(&tA0, s0.base, s0.C, s0.stride, p.WD, p.HT, p.E, p.TW, box_rows); if (rc) return rc;
   if (s1.base) { rc = make_act_map(&tA1, s1.base, s1.C, s1.stride, p.WD, p.HT, p.E, p.TW, box_rows); if (rc) return rc; }
   else tA1 = tA0;
-  rc = make_weight_map(&tW, wpk, 64 * (p.nk0 + p.nk1), p.n_ntiles * p.N, p.KS * p.KS, p.boxn); if (rc) return rc;
+  rc = make_weight_map(&tW, wpk, 64 * (p.nk0 + p.nk1), p.w_rows > 0 ? p.w_rows : p.n_ntiles * p.N, p.KS * p.KS, p.boxn); if (rc) return rc;
   static int attr_set = 0;
   if (attr_set < smem) {
     DBA_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "conv_tc smem attr");
@@ -668,10 +690,7 @@ extern "C" int dba_update_forward(const dba_update_args* a) {
     else if (a->corr_dtype == DBA_F32) nchw_to_nhwc_kernel<float><<<g, 256, 0, st>>>((const float*)a->corr, Cc, 196, HW, 200, 200);
     else { set_error("invalid argument: corr dtype must be f16 or f32"); return DBA_ERR_INVALID; }
   }
-  {
-    const size_t total = (size_t)E * HW * 50;
-    flow_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a->flow, F0, ht, wd, total);
-  }
+  flow_im2col_kernel<<<dim3((wd + 63) / 64, ht, E), 256, 0, st>>>(a->flow, F0, ht, wd);
   DBA_CHECK_LAUNCH("update layout kernels");
 
   ConvParams base;
@@ -704,7 +723,7 @@ extern "C" int dba_update_forward(const dba_update_args* a) {
     rc = launch_conv<EPI_Q>(p, ConvSrc{RH, 128, 128}, ConvSrc{X, 320, 320}, W->w_q, st); if (rc) return rc; }
   // ---- heads: stems delta.0 | weight.0 | agg.conv1 as one 384-output convolution + ReLU (droid_net.py:95-106, :60)
   const int stemN = n_src > 0 ? 384 : 256;
-  { ConvParams p = base; p.KS = 3; p.N = stemN; p.bias = W->b_stem; p.relu = 1; p.out = S; p.out_stride = 384;
+  { ConvParams p = base; p.KS = 3; p.N = stemN; p.w_rows = 384; p.bias = W->b_stem; p.relu = 1; p.out = S; p.out_stride = 384;
     rc = launch_conv<EPI_STORE>(p, ConvSrc{a->net_out, 128, 128}, none, W->w_stem, st); if (rc) return rc; }
   // delta.2 and weight.2 (3x3 128->2 each) as one block-diagonal 256->4 convolution; sigmoid on the weight
   { ConvParams p = base; p.KS = 3; p.N = 32; p.bias = W->b_heads; p.f32a = a->delta; p.f32b = a->weight; p.head_mode = 0;

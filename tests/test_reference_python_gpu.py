@@ -66,7 +66,8 @@ def test_corrblock_lookups_match_reference_classes(backends, gold):
         o, = backends.altcorr_forward(fmd, f[None].contiguous(), (ca_d / 2 ** l).contiguous(), ii.to(dev), jj.to(dev), 3)
         lv.append(o.flatten(2, 3))
         f = torch.nn.functional.avg_pool2d(f, 2, stride=2)
-    assert torch.equal(torch.stack(lv, dim=2).flatten(2, 3).cpu(), gold["altcorrblock_lookup"])
+    got = torch.stack(lv, dim=2).flatten(2, 3).cpu()                   # f32 dot products over 16 channels: summation order differs from the CPU run
+    assert got.shape == gold["altcorrblock_lookup"].shape and torch.allclose(got, gold["altcorrblock_lookup"], rtol=1e-5, atol=1e-5)
 
 
 def test_corr_volume_hook_replaces_the_constructor_only(backends):
