@@ -40,19 +40,48 @@ FRAMES = 72
 HT, WD = 48, 64
 RADIUS, LEVELS = 3, 4
 BA_ITERS, LM, EP = 2, 1e-4, 0.1
+CFG_NAME, SCALING, STEREO, WITH_CORR, RGBD = "metric", "weak", False, True, False
+
+# BASELINE.json `configs`.  `metric` is the configuration the metric is quoted on (and the default); the others
+# are selected with --config.  weak: `edges` per GPU (the graph grows with the GPU count over the same window); strong: `edges` in
+# total, sharded by source frame over the GPUs.
+CONFIGS = {
+    "metric": dict(edges=512, frames=72, ht=48, wd=64, dtype="f16", itrs=2, lm=1e-4, ep=0.1, scaling="weak", corr=True, stereo=False),
+    "c2": dict(edges=128, frames=25, ht=48, wd=64, dtype="f32", itrs=2, lm=1e-4, ep=0.1, scaling="weak", corr=True, stereo=False),
+    "c3": dict(edges=2048, frames=400, ht=48, wd=64, dtype="f16", itrs=10, lm=1e-5, ep=1e-2, scaling="strong", corr=False, stereo=False),
+    "c4": dict(edges=256, frames=64, ht=48, wd=64, dtype="f16", itrs=2, lm=1e-4, ep=0.1, scaling="weak", corr=True, stereo=True),
+    "c5": dict(edges=8192, frames=1000, ht=72, wd=96, dtype="bf16", itrs=2, lm=1e-4, ep=0.1, scaling="strong", corr=True, stereo=False),
+}
+
+
+def select_config(args):
+    """--config: BASELINE.json configs 2-5 at their stated sizes (the step keeps its definition: lookups over the rank's edges, if the
+    config has correlation volumes, + one ba call with the config's iteration count and damping)"""
+    global EDGES_PER_GPU, FRAMES, HT, WD, BA_ITERS, LM, EP, CFG_NAME, SCALING, STEREO, WITH_CORR
+    c = CONFIGS[args.config]
+    CFG_NAME, SCALING, STEREO, WITH_CORR = args.config, c["scaling"], c["stereo"], c["corr"]
+    EDGES_PER_GPU, FRAMES, HT, WD, BA_ITERS, LM, EP = c["edges"], c["frames"], c["ht"], c["wd"], c["itrs"], c["lm"], c["ep"]
+    if args.dtype is None:
+        args.dtype = c["dtype"]
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 400 for the metric config = a >= 0.5 s timed region; 20 otherwise)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default="f16", choices=["f16", "f32"])
+    ap.add_argument("--config", default="metric", choices=sorted(CONFIGS.keys()), help="BASELINE.json config (default: the one the metric is quoted on)")
+    ap.add_argument("--dtype", default=None, choices=["f16", "f32", "bf16"], help="correlation volume dtype (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-to-peer reduction inside the solve kernel (default) or a NCCL all-reduce of the pose system")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph (N=1)")
-    return ap.parse_args()
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernels (update operator, volume build, altcorr, geometry, solve) timed for `rooflines`")
+    args = ap.parse_args()
+    select_config(args)
+    if args.steps is None:
+        args.steps = 400 if (args.config == "metric" and args.impl == "ours") else 20
+    return args
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -123,15 +152,22 @@ def roofline_traffic():
 def build_problem(args, rank, world, dev):
     """the rank's shard of the (512*world)-edge graph: BA tensors, correlation pyramid, lookup coordinates"""
     from droid_slam_b200 import sharded, synth
-    cfg = dict(E=EDGES_PER_GPU * world, N=FRAMES, ht=HT, wd=WD, stereo=False, itrs=BA_ITERS, lm=LM, ep=EP)
+    cfg = dict(E=EDGES_PER_GPU * (world if SCALING == "weak" else 1), N=FRAMES, ht=HT, wd=WD, stereo=STEREO, itrs=BA_ITERS, lm=LM, ep=EP)
     s = synth.make_scene(cfg, seed=0)
     bounds = sharded.partition_frames(s["ii"], FRAMES, world)
     lo, hi = bounds[rank]
     idx = sharded.shard_edges(s["ii"], lo, hi)
-    dtype = torch.float16 if args.dtype == "f16" else torch.float32
+    dtype = {"f16": torch.float16, "f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
     sub = dict(s); sub["ii"] = s["ii"][idx]; sub["jj"] = s["jj"][idx]; sub["coords_gt"] = s["coords_gt"][idx]
     sub["cfg"] = dict(cfg, E=int(idx.numel()))
-    pyr, coords, _ = synth.make_corr_inputs(sub, dtype=dtype, device=dev, edge_chunk=32)
+    if WITH_CORR:
+        need = int(idx.numel()) * (HT * WD) ** 2 * 1.33 * (4 if dtype == torch.float32 else 2)
+        free = torch.cuda.mem_get_info(dev)[0]
+        if need > 0.9 * free:
+            raise SystemExit("config %s: %.0f GB of correlation volumes per GPU do not fit (%.0f GB free); use more GPUs" % (CFG_NAME, need / 1e9, free / 1e9))
+        pyr, coords, _ = synth.make_corr_inputs(sub, dtype=dtype, device=dev, edge_chunk=32 if HT * WD <= 3072 else 4)
+    else:
+        pyr, coords = [], torch.zeros(int(idx.numel()), 2, HT, WD, device=dev)
     kx = torch.unique(torch.cat([torch.arange(s["t0"], s["t1"]), s["ii"]]))
     eta_f = torch.zeros(FRAMES, HT, WD); eta_f[kx] = s["eta"]
     host = dict(poses=s["poses"], disps=s["disps"], disps_sens=s["disps_sens"], intrinsics=s["intrinsics"], targets=s["targets"][idx].contiguous(),
@@ -141,7 +177,7 @@ def build_problem(args, rank, world, dev):
 
 
 def alg_bytes_corr(E, dtype):
-    s = 2 if dtype == torch.float16 else 4
+    s = 4 if dtype == torch.float32 else 2
     return E * HT * WD * (LEVELS * ((2 * RADIUS + 2) ** 2 + (2 * RADIUS + 1) ** 2) * s + LEVELS * 8)     # HW*(452 s + 32)
 
 
@@ -154,11 +190,12 @@ def run_ours(args, rank, world, dev):
     pb = build_problem(args, rank, world, dev)
     h = pb["host"]
     E, dtype = pb["E"], pb["dtype"]
-    dcode = c_api.DBA_F16 if dtype == torch.float16 else c_api.DBA_F32
+    dcode = {torch.float16: c_api.DBA_F16, torch.float32: c_api.DBA_F32, torch.bfloat16: c_api.DBA_BF16}[dtype]
     d = {k: v.to(dev) for k, v in h.items()}
     pristine_poses, pristine_disps = d["poses"].clone(), d["disps"].clone()
-    coords_l = [(pb["coords"] / 2 ** l).contiguous() for l in range(LEVELS)]
-    corr_out = [torch.empty(E, 7, 7, HT, WD, dtype=dtype, device=dev) for _ in range(LEVELS)]
+    NL = LEVELS if WITH_CORR else 0
+    coords_l = [(pb["coords"] / 2 ** l).contiguous() for l in range(NL)]
+    corr_out = [torch.empty(E, 7, 7, HT, WD, dtype=dtype, device=dev) for _ in range(NL)]
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
     spbox = [sp]
@@ -179,7 +216,7 @@ def run_ours(args, rank, world, dev):
     def step_resident(ev=None):
         d["poses"].copy_(pristine_poses); d["disps"].copy_(pristine_disps)
         if ev: ev[0].record()
-        for l in range(LEVELS):
+        for l in range(NL):
             v = pb["pyr"][l]
             c_api.check(L.dba_corr_index_forward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(coords_l[l].data_ptr()),
                                                  ctypes.c_void_p(corr_out[l].data_ptr()), E, HT, WD, v.shape[3], v.shape[4], RADIUS, dcode, spbox[0]), "corr")
@@ -267,7 +304,7 @@ def run_ours(args, rank, world, dev):
             g = {k: pin[k].to(dev, non_blocking=True) for k in pin if k not in ("eta", "eta_by_frame", "coords")}
             eta = (pin["eta"] if world == 1 else pin["eta_by_frame"]).to(dev, non_blocking=True)
         feats = []
-        for l in range(LEVELS):
+        for l in range(NL):
             corr, = be.corr_index_forward(pb["pyr"][l], coords / 2 ** l, RADIUS)       # reference call pattern, modules/corr.py:46-48
             feats.append(corr)
         main.wait_stream(copy_stream)
@@ -316,7 +353,7 @@ def run_ours(args, rank, world, dev):
                 for k in stat:
                     if k != "coords":
                         stat[k].copy_(pin[k], non_blocking=True)
-            keep = [be.corr_index_forward(pb["pyr"][l], stat["coords"] / 2 ** l, RADIUS)[0] for l in range(LEVELS)]
+            keep = [be.corr_index_forward(pb["pyr"][l], stat["coords"] / 2 ** l, RADIUS)[0] for l in range(NL)]
             main.wait_stream(copy_stream)
             if world == 1:
                 dx, dz = be.ba(stat["poses"], stat["disps"], stat["intrinsics"], stat["disps_sens"], stat["targets"], stat["weights"], stat["eta"],
@@ -341,67 +378,178 @@ def run_ours(args, rank, world, dev):
         return
     peak, peak_src = measured_peak()
     alg = alg_bytes_corr(E, dtype)
-    achieved = alg / (corr_ms * 1e-3) / 1e9
+    achieved = alg / (corr_ms * 1e-3) / 1e9 if (WITH_CORR and corr_ms > 0) else 0.0
     traffic = roofline_traffic()
-    launches_per_step = LEVELS + 2 + BA_ITERS * 6        # corr x4, prepare+csr, per GN iter: build, schur x2, chol, backsub, pose_retr
+    launches_per_step = NL + 2 + BA_ITERS * 6        # corr x4, prepare+csr, per GN iter: build, schur x2, chol, backsub, pose_retr
+    Ptot = pb["t1"] - pb["t0"]
+    sys_bytes = 8 * (36 * Ptot * Ptot + 6 * Ptot)
+    mult = world if SCALING == "weak" else 1
+    if CFG_NAME == "metric":
+        metric, unit = "BA-update iters/sec (512 edges, 344x64x48)", "iters/s (512-edge equivalents)"
+        workload = "metric: %d edges/GPU x %d GPU(s) over a %d-keyframe window at %dx%d, 4-level r=3 corr_index_forward + ba(itrs=2, lm=1e-4, ep=0.1)" % (EDGES_PER_GPU, world, FRAMES, HT, WD)
+    else:
+        metric, unit = "BA-update iters/sec (BASELINE config %s)" % CFG_NAME, "iters/s (one step = %sba(itrs=%d))" % ("4-level corr_index_forward + " if WITH_CORR else "", BA_ITERS)
+        workload = "%s: %d edges %s, %d keyframes at %dx%d, %s volumes, %sba(itrs=%d, lm=%g, ep=%g)%s" % (
+            CFG_NAME, EDGES_PER_GPU, "per GPU" if SCALING == "weak" else "in total (sharded over %d GPU(s))" % world, FRAMES, HT, WD, args.dtype,
+            "4-level r=3 corr_index_forward + " if WITH_CORR else "no lookup (global BA backend), ", BA_ITERS, LM, EP, ", one (i,i) stereo edge per frame" if STEREO else "")
     line = {
-        "metric": "BA-update iters/sec (512 edges, 344x64x48)", "value": world * 1e3 / ms_step, "unit": "iters/s (512-edge equivalents)",
+        "metric": metric, "value": mult * 1e3 / ms_step, "unit": unit,
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (BA solve in f64), %s corr volumes" % args.dtype, "data": "synthetic",
+        "scaling": SCALING, "vs_baseline": None, "dtype": "f32 (BA solve in f64), %s corr volumes" % args.dtype, "data": "synthetic",
         "impl": "ours",
-        "config": {"workload": "metric: %d edges/GPU x %d GPU(s) over a %d-keyframe window at %dx%d, 4-level r=3 corr_index_forward + ba(itrs=2, lm=1e-4, ep=0.1)"
-                               % (EDGES_PER_GPU, world, FRAMES, HT, WD),
-                   "edges_this_rank": E, "frames": FRAMES, "depth_frames": pb["M"], "pose_system": 6 * (pb["t1"] - pb["t0"]),
+        "config": {"workload": workload, "name": CFG_NAME,
+                   "edges_this_rank": E, "frames": FRAMES, "depth_frames": pb["M"], "pose_system": 6 * Ptot,
                    "parallelism": ("edge-sharded by source frame; the %d-double pose system is reduced once per GN iteration, %s" % (36 * P * P + 6 * P, "fused into the Cholesky kernel (peer-to-peer loads over NVLink, release/acquire flags)" if p2p is not None else "NCCL all-reduce")) if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2: %.1f GB of correlation volumes stream through the 126 MB L2 every step" % (sum(v.numel() * v.element_size() for v in pb["pyr"]) / 1e9)},
-        "e2e": {"value": world * 1e3 / e2e_ms, "unit": "iters/s (512-edge equivalents)", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "l2": ("inputs larger than L2: %.1f GB of correlation volumes stream through the 126 MB L2 every step" % (sum(v.numel() * v.element_size() for v in pb["pyr"]) / 1e9)) if WITH_CORR else
+                         "BA inputs of %.0f MB per rank; L2 not flushed between steps (the reference keeps them resident too)" % (E * HT * WD * 16 / 1e6)},
+        "e2e": {"value": mult * 1e3 / e2e_ms, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "launch_mode": e2e_mode, "eager_ms_per_step": e2e_eager_ms, "h2d_copy_only_ms": copy_only_ms,
                 "api": "droid_backends.corr_index_forward x4 + droid_backends.ba from pinned host buffers (BA inputs copied on a second stream during the lookups); volumes persistent on device"},
         "gpu_launches": launches_per_step * args.steps, "launch_mode": "cuda graph replay" if graph is not None else "eager",
         "clocks": clocks,
-        "roofline": {"kernel": "corr_index_fwd_%s_r3_kernel (4 launches/step)" % args.dtype, "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
-                     "kernel_ms_per_step": corr_ms, "share_of_step": corr_ms / ms_step,
-                     "traffic": (traffic or {}).get("dram_bytes_per_step_" + args.dtype)},
-        "ba_ms_per_step": ms_step - corr_ms,
+        "ba_ms_per_step": ms_step - corr_ms, "ms_per_gn_iteration": (ms_step - corr_ms) / BA_ITERS,
+        "pose_system_reduction": {"bytes_per_gn_iteration": sys_bytes, "nvlink_bytes_per_gn_iteration_per_gpu": (sys_bytes * (world - 1) if p2p is not None else int(2 * sys_bytes * (world - 1) / max(world, 1))) if world > 1 else 0,
+                                  "how": ("every rank reads the %d peer copies inside the solve kernel" % (world - 1)) if p2p is not None else ("NCCL ring all-reduce (2(N-1)/N x bytes per GPU)" if world > 1 else "none")},
     }
-    if world == 1:
-        line["update_operator"] = update_operator_library_ms(E, dev, ms_step)
-    if world == 1 and not args.no_cpu_baseline:
+    if WITH_CORR:
+        line["roofline"] = {"kernel": "corr_index_fwd_%s_r3_kernel (4 launches/step)" % args.dtype, "bound": "hbm", "achieved": achieved, "peak": peak,
+                            "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                            "kernel_ms_per_step": corr_ms, "share_of_step": corr_ms / ms_step,
+                            "traffic": (traffic or {}).get("dram_bytes_per_step_" + args.dtype),
+                            "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the four launches, profiles/ (captured once per kernel change, not re-measured by this run)"}
+    else:
+        alg_ba = BA_ITERS * (16 * E * HT * WD + 16 * pb["M"] * HT * WD + 28 * FRAMES)
+        line["roofline"] = {"kernel": "ba (build + Schur + solve + back-substitution per GN iteration)", "bound": "hbm", "achieved": alg_ba / ((ms_step - corr_ms) * 1e-3) / 1e9,
+                            "peak": peak, "unit": "GB/s", "frac": alg_ba / ((ms_step - corr_ms) * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                            "algorithmic_bytes_per_step": alg_ba, "traffic": None,
+                            "note": "SURVEY 8d BA bytes (16 E HW + 16 M HW + 28 N per iteration); the step is latency / solve bound, not HBM bound"}
+    if world == 1 and not args.no_extras:
+        extras = secondary_kernels(E, dev, ms_step, L, be)
+        line["update_operator"] = extras.pop("update_operator")
+        line["rooflines"] = extras["rooflines"]
+    if world == 1 and not args.no_cpu_baseline and CFG_NAME in ("metric", "c2", "c4"):
         line["cpu_baseline"] = cpu_baseline(pb)
     print(json.dumps(line))
 
 
-def update_operator_library_ms(E, dev, ms_step, iters=5):
-    """the full update = this step + the update operator.  The operator here is the LIBRARY baseline of row A6
-    (droid_slam_b200/update.py: torch/cuDNN convolutions under fp16 autocast like factor_graph.py:214), reported for context only --
-    it is not one of this repo's kernels and is not part of `value`.  Any failure is reported, never raised."""
+def _time_ms(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def secondary_kernels(E, dev, ms_step, L, be):
+    """The other kernels of the path, each timed on its own with CUDA events (not part of `value`): the update operator (row A6,
+    tcgen05 convolutions), the correlation-volume build (A7), altcorr (A2), the streaming geometry ops (A8-A11) and the fp64 solve.
+    Each entry carries its algorithmic work and the roofline it is held against.  Failures are reported, never raised."""
+    out = {"update_operator": None, "rooflines": []}
+    peaks = {}
     try:
-        from droid_slam_b200 import synth
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    tf_burst, tf_sust = float(peaks.get("bf16_tflops", 1590.0)), float(peaks.get("bf16_tflops_sustained", 1400.0))
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    from droid_slam_b200 import synth
+    g = torch.Generator(device=dev).manual_seed(7)
+    # ---- update operator: same E edges as the step, 72 source frames
+    try:
         from droid_slam_b200.update import UpdateModule
-        mod = UpdateModule().to(dev).eval()
+        mod = UpdateModule().to(dev)
         mod.load_state_dict({k: v.to(dev) for k, v in synth.make_update_weights(0).items()})
-        g = torch.Generator(device=dev).manual_seed(7)
         net = torch.tanh(torch.randn(1, E, 128, HT, WD, generator=g, device=dev)).half()
         inp = torch.relu(torch.randn(1, E, 128, HT, WD, generator=g, device=dev)).half()
         corr = torch.randn(1, E, 196, HT, WD, generator=g, device=dev).half()
         motn = torch.randn(1, E, 4, HT, WD, generator=g, device=dev)
         ii = torch.arange(E, device=dev) % FRAMES
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
-            for _ in range(2):
-                mod(net, inp, corr, motn, ii)
-            torch.cuda.synchronize()
-            ev[0].record()
-            for _ in range(iters):
-                mod(net, inp, corr, motn, ii)
-            ev[1].record()
-        torch.cuda.synchronize()
-        ms = ev[0].elapsed_time(ev[1]) / iters
-        return {"ms": ms, "full_update_ms": ms + ms_step, "edges": E,
-                "impl": "library baseline (torch/cuDNN convolutions, fp16 autocast); not a hand-written kernel, not included in value"}
-    except Exception as e:                                   # context only: never fail the bench line
-        return {"ms": None, "error": str(e)[:200]}
+        with torch.no_grad():
+            ms = _time_ms(lambda: mod(net, inp, corr, motn, ii))
+        flops = (14.03e9 * E + 1.37e9 * min(E, FRAMES)) * (HT * WD / 3072.0)              # SURVEY 8d
+        out["update_operator"] = {"ms": ms, "full_update_ms": ms + ms_step, "edges": E, "tflops": flops / ms / 1e9,
+                                  "impl": "droid_slam_b200.UpdateModule: tcgen05 implicit-GEMM convolutions (csrc/update_op.cu), reference-layout (NCHW) inputs, f16 operands / fp32 accumulation; "
+                                          "not part of `value`; the reference formula through torch/cuDNN is timed by --impl reference"}
+        out["rooflines"].append({"kernel": "update operator (conv_tc_kernel x12 + layout / aggregation kernels)", "bound": "tensor", "achieved": flops / ms / 1e9, "peak": tf_sust, "unit": "TFLOP/s",
+                                 "frac": flops / ms / 1e9 / tf_sust, "peak_source": src + " bf16_tflops_sustained (a 10+ ms tensor-bound kernel sequence runs under the power cap)", "ms": ms,
+                                 "algorithmic_flops": flops})
+        del net, inp, corr, motn, mod
+    except Exception as e:
+        out["update_operator"] = {"ms": None, "error": str(e)[:200]}
+    # ---- correlation volume build (128 edges)
+    try:
+        if be.corr_volume_supported(128, HT, WD):
+            n_e = 128
+            fm = torch.randn(FRAMES, 128, HT, WD, generator=g, device=dev).half()
+            ii = torch.arange(n_e, device=dev) % FRAMES; jj = (ii + 1) % FRAMES
+            ms = _time_ms(lambda: be.corr_volume_pyramid(fm, fm, ii, jj))
+            byts = n_e * (HT * WD) ** 2 * 2 * 1.328125
+            out["rooflines"].append({"kernel": "corr_volume_pyramid_kernel (128 edges)", "bound": "hbm", "achieved": byts / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": byts / ms / 1e6 / hbm,
+                                     "peak_source": src, "ms": ms, "algorithmic_bytes": byts, "tflops": 2.0 * n_e * (HT * WD) ** 2 * 128 / ms / 1e9})
+            del fm
+    except Exception as e:
+        out["rooflines"].append({"kernel": "corr_volume_pyramid_kernel", "error": str(e)[:200]})
+    # ---- altcorr (48 edges, 4 levels)
+    try:
+        n_e = 48
+        fm = torch.randn(1, 16, 128, HT, WD, generator=g, device=dev).half()
+        pyr = [fm]
+        for _ in range(3):
+            pyr.append(torch.nn.functional.avg_pool2d(pyr[-1][0], 2, stride=2)[None].contiguous())
+        sc = synth.make_scene(dict(E=n_e, N=16, ht=HT, wd=WD, stereo=False, itrs=1, lm=1e-4, ep=0.1), seed=2)
+        coords = sc["coords_gt"].permute(0, 3, 1, 2)[None].contiguous().to(dev)
+        ii, jj = sc["ii"].to(dev), sc["jj"].to(dev)
+        cl = [(coords / 2 ** l).contiguous() for l in range(4)]
+        ms = _time_ms(lambda: [be.altcorr_forward(fm, pyr[l], cl[l], ii, jj, 3) for l in range(4)])
+        byts = n_e * (128 * HT * WD * 2 * (1 + 1.328125) + 8 * HT * WD * 4 + 4 * 49 * HT * WD * 2)
+        fl = 2.0 * 4 * HT * WD * 64 * 128 * n_e
+        out["rooflines"].append({"kernel": "altcorr_forward_kernel (48 edges x 4 levels)", "bound": "hbm", "achieved": byts / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": byts / ms / 1e6 / hbm,
+                                 "peak_source": src, "ms": ms, "algorithmic_bytes": byts, "tflops": fl / ms / 1e9,
+                                 "note": "compulsory bytes (SURVEY 8d); the kernel is a SIMT gather + 128-channel dot product, far from this bound"})
+        del fm, pyr
+    except Exception as e:
+        out["rooflines"].append({"kernel": "altcorr_forward_kernel", "error": str(e)[:200]})
+    # ---- streaming geometry at the step's scene size
+    try:
+        sc = synth.make_scene(dict(E=512, N=FRAMES, ht=HT, wd=WD, stereo=False, itrs=1, lm=1e-4, ep=0.1), seed=0)
+        P, D, K, ii, jj = [sc[k].to(dev) for k in ("poses", "disps", "intrinsics", "ii", "jj")]
+        hw = HT * WD
+        a, b = torch.meshgrid(torch.arange(FRAMES), torch.arange(FRAMES), indexing="ij")
+        a, b = a.reshape(-1).to(dev), b.reshape(-1).to(dev)
+        ix = torch.arange(FRAMES, device=dev); th = torch.full((FRAMES,), 0.05, device=dev)
+        for name, fn, byts in (("projmap_kernel (512 edges)", lambda: be.projmap(P, D, K, ii, jj), 512 * hw * 20),
+                               ("iproj_kernel (%d frames)" % FRAMES, lambda: be.iproj(P, D, K), FRAMES * hw * 16),
+                               ("frame_distance_kernel (%d pairs)" % (FRAMES * FRAMES), lambda: be.frame_distance(P, D, K, a, b, 0.3), FRAMES * FRAMES * hw * 4),
+                               ("depth_filter_kernel (%d frames)" % FRAMES, lambda: be.depth_filter(P, D, K, ix, th), FRAMES * hw * 8)):
+            ms = _time_ms(fn, iters=10)
+            out["rooflines"].append({"kernel": name, "bound": "hbm", "achieved": byts / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": byts / ms / 1e6 / hbm, "peak_source": src, "ms": ms,
+                                     "algorithmic_bytes": byts, "note": "L2-resident working set at this size: launch / latency bound"})
+    except Exception as e:
+        out["rooflines"].append({"kernel": "geometry ops", "error": str(e)[:200]})
+    # ---- fp64 damped solve at the step's system size
+    try:
+        n = 6 * (FRAMES - 1)
+        A = torch.randn(n, n, generator=g, device=dev, dtype=torch.float64)
+        H = (A @ A.t() + n * torch.eye(n, device=dev, dtype=torch.float64)).contiguous()
+        bvec = torch.randn(n, generator=g, device=dev, dtype=torch.float64)
+        x = torch.empty(n, device=dev); fail = torch.zeros(1, dtype=torch.int32, device=dev)
+        wsb = L.dba_solve_workspace_bytes(n)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        vp = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ms = _time_ms(lambda: L.dba_solve_spd(vp(H), vp(bvec), n, ctypes.c_float(1e-4), ctypes.c_float(0.1), vp(x), vp(fail), vp(ws), ctypes.c_size_t(wsb), st), iters=20)
+        fl = n ** 3 / 3.0
+        out["rooflines"].append({"kernel": "chol_cluster_kernel (n = %d, fp64)" % n, "bound": "fp64 issue rate", "achieved": fl / ms / 1e9, "peak": 34.0, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / 34.0,
+                                 "peak_source": "measured fp64 FMA issue rate (profiles/r1_fp64_issue_rate.txt)", "ms": ms, "algorithmic_flops": fl,
+                                 "note": "latency bound: a chain of n/32 dependent panel steps, the figure of merit is the time"})
+    except Exception as e:
+        out["rooflines"].append({"kernel": "chol_cluster_kernel", "error": str(e)[:200]})
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -450,7 +598,7 @@ def run_reference(args, rank, world, dev):
 
     def corr_all(coords):
         outs = []
-        for l in range(LEVELS):
+        for l in range(LEVELS if WITH_CORR else 0):
             c = coords / 2 ** l
             parts = [ref.corr_index_forward(pb["pyr"][l][s:s + CH], c[s:s + CH].contiguous(), RADIUS)[0] for s in range(0, E, CH)]
             outs.append(parts)
@@ -487,19 +635,44 @@ def run_reference(args, rank, world, dev):
     ms_step, solve_ms = timed(step_resident, args.steps, max(args.warmup, 3))
     clocks = sampler.stop()
     e2e_ms, _ = timed(step_e2e, args.steps, 2)
+    if CFG_NAME == "metric":
+        metric, unit = "BA-update iters/sec (512 edges, 344x64x48)", "iters/s (512-edge equivalents)"
+    else:
+        metric, unit = "BA-update iters/sec (BASELINE config %s)" % CFG_NAME, "iters/s (one step = %sba(itrs=%d))" % ("4-level corr_index_forward + " if WITH_CORR else "", BA_ITERS)
+    upd = reference_update_operator_ms(E, dev) if (CFG_NAME == "metric" and not args.no_extras) else None
     line = {
-        "metric": "BA-update iters/sec (512 edges, 344x64x48)", "value": 1e3 / ms_step, "unit": "iters/s (512-edge equivalents)", "n_gpus": 1,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (CPU solve in f64), %s corr volumes" % args.dtype, "data": "synthetic", "impl": "reference",
-        "config": {"workload": "metric: 512 edges over a %d-keyframe window at %dx%d, 4-level r=3 corr_index_forward (chunks of %d edges: 32-bit accessors) + ba(itrs=2)" % (FRAMES, HT, WD, CH),
+        "metric": metric, "value": 1e3 / ms_step, "unit": unit, "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
+        "dtype": "f32 (CPU solve in f64), %s corr volumes" % args.dtype, "data": "synthetic", "impl": "reference", "update_operator": upd,
+        "config": {"workload": "%s: %d edges over a %d-keyframe window at %dx%d, %s + ba(itrs=%d, lm=%g, ep=%g)" % (CFG_NAME, E, FRAMES, HT, WD, ("4-level r=3 corr_index_forward (chunks of %d edges: 32-bit accessors)" % CH) if WITH_CORR else "no lookup", BA_ITERS, LM, EP), "name": CFG_NAME,
                    "implementation": "unmodified /root/reference/src/*.cu + droid.cpp built for sm_100a (oracle/build_ref.sh); CPU solve = dense fp64 LLT stand-in for Eigen::SimplicialLLT",
                    "cpu_solve_ms_per_step": solve_ms, "ms_per_step_without_cpu_solve": ms_step - solve_ms},
-        "e2e": {"value": 1e3 / e2e_ms, "unit": "iters/s (512-edge equivalents)", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": 1e3 / e2e_ms, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "cpu_baseline": {"value": 1e3 / ms_step, "unit": "iters/s", "cores": os.cpu_count(), "kind": "reference",
                          "sample": "full workload, %d steps; the reference path is CUDA kernels + a host-side sparse-block solve (its CPU part uses 1 thread)" % args.steps},
         "clocks": clocks,
     }
     print(json.dumps(line))
+
+
+def reference_update_operator_ms(E, dev, iters=3):
+    """the reference's update operator formula (droid_net.py:111-143 as restated in oracle/update.py, pinned bit-exactly against the
+    reference module) through torch/cuDNN under fp16 autocast like factor_graph.py:214 -- what `update_operator` of our arm replaces"""
+    try:
+        import oracle
+        from droid_slam_b200 import synth
+        w = {k: v.to(dev) for k, v in synth.make_update_weights(0).items()}
+        g = torch.Generator(device=dev).manual_seed(7)
+        net = torch.tanh(torch.randn(1, E, 128, HT, WD, generator=g, device=dev)).half()
+        inp = torch.relu(torch.randn(1, E, 128, HT, WD, generator=g, device=dev)).half()
+        corr = torch.randn(1, E, 196, HT, WD, generator=g, device=dev).half()
+        motn = torch.randn(1, E, 4, HT, WD, generator=g, device=dev)
+        ii = torch.arange(E, device=dev) % FRAMES
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            ms = _time_ms(lambda: oracle.update_module_forward(w, net, inp, corr, motn, ii), iters=iters)
+        return {"ms": ms, "edges": E, "impl": "reference formula (oracle/update.py) through torch/cuDNN convolutions under fp16 autocast"}
+    except Exception as e:
+        return {"ms": None, "error": str(e)[:200]}
 
 
 def run_reference_cpu(args, dev, why):
@@ -530,7 +703,6 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version banner at INFO/VERSION)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         if args.impl == "reference":

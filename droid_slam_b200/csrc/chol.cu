@@ -15,6 +15,11 @@
 //     warp inverts L_kk for the backward pass
 //       -- cluster barrier --
 // i.e. two hardware cluster barriers per panel instead of kernel launches or grid-wide syncs.
+// ENVELOPE: the reduced pose system of a sliding-window / proximity factor graph is block banded (pose a couples to pose b only
+// through a common source frame), and a Cholesky factor never fills in left of a row's first nonzero.  The load phase records, per
+// 32-row tile row, the first structurally nonzero tile column (`first`); TRSM, trailing updates and the backward substitution then
+// skip every tile outside that envelope.  A dense system (the 72-keyframe metric window) does the same work as before; the global-BA
+// configs (6P = 2394 ... 5994, half bandwidth ~150) drop from O(n^3) to O(n b^2) -- what Eigen's sparse LLT does for the reference.
 // The right-hand side rides along as an extra tile row, so L^-1 b comes out of the factorisation for free; the
 // backward substitution uses the inverted diagonal tiles and runs in CTA 0.
 // (B200 note, measured: a dependent fp64 op costs ~10-20 cycles and a 64-bit warp shuffle pair is slower than a
@@ -86,6 +91,7 @@ struct CholParams {
   double* L;         // [(nt+1)*32][nt*32] row-major working matrix (tile row nt carries b^T in its row 0)
   double* Linv;      // [nt][32][32] inverses of the diagonal tiles
   double* rdiag;     // [nt*32] reciprocals of diag(L)
+  int* first;        // [nt+1] envelope: first nonzero tile column of each tile row (rhs row nt: 0)
   int* fail;         // sticky flag: non-positive pivot
   float* x;          // [n] result (fp32 like the reference's dx)
   int n, nt;
@@ -143,6 +149,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
   __shared__ double s_rdiag[kT];
   __shared__ double s_vec[kT];
   __shared__ double s_col[2 * kT];
+  __shared__ int s_act[kCholThreads];                // tile rows with a nonzero tile in panel k (ascending; the rhs row nt is always last)
+  __shared__ int s_wc[kCholWarps];
+  __shared__ int s_nact;
   extern __shared__ double s_dyn[];                  // per-warp slabs + two CTA-wide tiles, rows padded to 33 doubles
   double (*s_A)[kT][kTP] = reinterpret_cast<double (*)[kT][kTP]>(s_dyn);
   double (*s_B)[kT][kTP] = reinterpret_cast<double (*)[kT][kTP]>(s_dyn + (size_t)kCholWarps * kT * kTP);
@@ -169,6 +178,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     __syncthreads();
     if (cta == 0 && tid == 0) *p.fail = s_timeout ? 2 : 0;   // a peer never arrived: give up loudly (dx = 0), never hang
   } else if (cta == 0 && tid == 0) *p.fail = 0;
+  // ---- envelope: first[i] starts at the diagonal, the load below lowers it to the first nonzero tile of the row
+  const bool envelope = nt < kCholThreads;             // one thread per tile row in the per-panel scan below
+  for (int i = cta * kCholThreads + tid; i <= nt; i += ncta * kCholThreads) p.first[i] = (i < nt && envelope) ? i : 0;
+  cluster.sync();
   // ---- load: lower tiles of H with damping (reference :1205-1206), identity padding, rhs row ------------------
   {
     const size_t total = (size_t)(nt + 1) * kT * ld;
@@ -198,6 +211,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
             if (q < world) v += t[q];
         } else v = (src < nn) ? p.H[src] : p.b[src - nn];
         if (src < nn && r == c) v += p.ep + p.lm * v;
+        if (envelope && v != 0.0 && r < nt * kT) {
+          const int tr = r >> 5, tc = c >> 5;
+          if (tc < tr && tc < *reinterpret_cast<volatile int*>(p.first + tr)) atomicMin(p.first + tr, tc);
+        }
       }
       stcg(L + idx, v);
     }
@@ -226,10 +243,24 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       s_Lkk[r][c] = ldcg(L + (size_t)(k * kT + r) * ld + k * kT + c);
     }
     if (tid < kT) s_rdiag[tid] = ldcg(p.rdiag + k * kT + tid);
+    // active tile rows of panel k (inside the envelope), in ascending order -- every CTA builds the identical list
+    {
+      const int i_row = k + 1 + tid;
+      const bool act = envelope ? (i_row <= nt && (i_row == nt || __ldcg(p.first + i_row) <= k)) : false;
+      const unsigned bal = __ballot_sync(0xffffffffu, act);
+      if (lane == 0) s_wc[warp] = __popc(bal);
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < warp; w++) base += s_wc[w];
+      if (act) s_act[base + __popc(bal & ((1u << lane) - 1u))] = i_row;
+      if (tid == 0) { int tot = 0; for (int w = 0; w < kCholWarps; w++) tot += s_wc[w]; s_nact = tot; }
+    }
     __syncthreads();
+    const int nact = envelope ? s_nact : (nt - k);       // >= 1: the rhs row
     CHOL_STAMP(8 + 8 * k + 0);
-    // ---- TRSM: tiles (i,k), i = k+1 .. nt (tile row nt is the right-hand side)
-    for (int i = k + 1 + gw; i <= nt; i += nwarps) {
+    // ---- TRSM: tiles (i,k) of the active rows (tile row nt is the right-hand side)
+    for (int ta = gw; ta < nact; ta += nwarps) {
+      const int i = envelope ? s_act[ta] : k + 1 + ta;
       double a[kT];
       double* tile = L + (size_t)(i * kT) * ld + k * kT;
 #pragma unroll
@@ -258,8 +289,12 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     CHOL_STAMP(8 + 8 * k + 2);
     // ---- trailing update with panel k
     const int rem = nt - k - 1;                       // remaining tile columns
-    const int ntri = rem * (rem + 1) / 2;
-    const int ntasks = ntri + rem;                    // tiles (i,j), k<j<=i<nt, plus the rhs row tiles (nt,j)
+    const int m1 = nact - 1;                          // active rows without the rhs row
+    const int ntri = m1 * (m1 + 1) / 2;
+    const int ntasks = ntri + m1;                     // tiles (i,j) of active rows, j <= i < nt, plus the rhs row tiles (nt,j)
+    // task 0 = tile (k+1,k+1) when row k+1 is active: CTA 0 updates + factors it below; otherwise that tile needs no update (CTA 0 still
+    // factors it) and task 0 is an ordinary tile of the workers
+    const bool diag_active = envelope ? (m1 >= 1 && s_act[0] == k + 1) : (rem >= 1);
     if (cta == 0 && rem >= 1) {
       // next diagonal tile (task 0): all 256 threads update it, warp 0 factors it
       const double* At = L + (size_t)((k + 1) * kT) * ld + k * kT;
@@ -302,15 +337,15 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     }
     // remaining tiles: every warp of the cluster except the factoring one
     if (gw != 0) {
-      for (int t = gw; t < ntasks; t += nwarps - 1) {      // tasks 1..ntasks-1 over workers 1..nwarps-1
+      for (int t = (diag_active ? 1 : 0) + gw - 1; t < ntasks; t += nwarps - 1) {
         int i, j;
         if (t < ntri) {
           int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
           while (bi * (bi + 1) / 2 > t) bi--;
           while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
           const int bj = t - bi * (bi + 1) / 2;
-          i = k + 1 + bi; j = k + 1 + bj;
-        } else { i = nt; j = k + 1 + (t - ntri); }
+          i = envelope ? s_act[bi] : k + 1 + bi; j = envelope ? s_act[bj] : k + 1 + bj;
+        } else { i = nt; j = envelope ? s_act[t - ntri] : k + 1 + (t - ntri); }
         warp_tile_update(L + (size_t)(i * kT) * ld + k * kT, L + (size_t)(j * kT) * ld + k * kT, L + (size_t)(i * kT) * ld + j * kT, ld, lane,
                          s_A[warp], s_B[warp]);
       }
@@ -347,8 +382,8 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       s_vec[lane] = s;
     }
     __syncthreads();
-    // y_i -= L_ki^T x_k  for i < k : lane = column of tile (k,i)
-    for (int i = warp; i < k; i += kCholWarps) {
+    // y_i -= L_ki^T x_k  for first[k] <= i < k (tiles left of the envelope are zero): lane = column of tile (k,i)
+    for (int i = __ldcg(p.first + k) + warp; i < k; i += kCholWarps) {
       double s = 0.0;
 #pragma unroll 8
       for (int r = 0; r < kT; r++) s += ldcg(L + (size_t)(k * kT + r) * ld + i * kT + lane) * s_vec[r];
@@ -367,7 +402,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
 size_t chol_workspace_bytes(int n) {
   const size_t nt = (size_t)(n + kT - 1) / kT;
   const size_t ld = nt * kT;
-  return ((nt + 1) * kT * ld + nt * kT * kT + nt * kT) * sizeof(double) + 256;
+  return ((nt + 1) * kT * ld + nt * kT * kT + nt * kT) * sizeof(double) + (nt + 2) * sizeof(int) + 256;
 }
 
 // H [n][n] fp64, b [n] fp64 -> x [n] fp32; fail flag is a device int
@@ -381,6 +416,7 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   p.L = reinterpret_cast<double*>(workspace);
   p.Linv = p.L + (size_t)(p.nt + 1) * kT * ld;
   p.rdiag = p.Linv + (size_t)p.nt * kT * kT;
+  p.first = reinterpret_cast<int*>(p.rdiag + (size_t)p.nt * kT);
 
   const size_t dyn_smem = ((size_t)2 * kCholWarps + 2) * kT * kTP * sizeof(double);
   static int cluster_size = 0;

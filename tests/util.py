@@ -64,3 +64,13 @@ def rel_err(a, b, floor=1.0):
 def frac_equal(a, b):
     a = a.cpu(); b = b.cpu()
     return float((a == b).float().mean())
+
+
+def assert_bit_identical(a, b, what=""):
+    """torch.equal with a useful message (how many elements differ and by how much)"""
+    a = a.cpu(); b = b.cpu()
+    assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
+    if not torch.equal(a, b):
+        neq = (a != b) & ~(torch.isnan(a) & torch.isnan(b))
+        d = (a.double() - b.double()).abs()
+        raise AssertionError("%s: %d of %d elements differ, max |diff| %.3e" % (what, int(neq.sum()), a.numel(), float(d[neq].max()) if bool(neq.any()) else 0.0))
