@@ -76,6 +76,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-to-peer reduction inside the solve kernel (default) or a NCCL all-reduce of the pose system")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph (N=1)")
+    ap.add_argument("--dropin-lookup", action="store_true", help="time the step with the four drop-in corr_index_forward launches on reference-layout volumes (round-1 definition) instead of the fused one-launch lookup on tiled volumes")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernels (update operator, volume build, altcorr, geometry, solve) timed for `rooflines`")
     args = ap.parse_args()
     select_config(args)
@@ -196,6 +197,16 @@ def run_ours(args, rank, world, dev):
     NL = LEVELS if WITH_CORR else 0
     coords_l = [(pb["coords"] / 2 ** l).contiguous() for l in range(NL)]
     corr_out = [torch.empty(E, 7, 7, HT, WD, dtype=dtype, device=dev) for _ in range(NL)]
+    # fused lookup (CorrBlock.__call__ in one launch, droid_slam_b200.modules.install_corr_volume_hook(fused_lookup=True)): levels 0 and 1 of
+    # the volumes in the tiled layout corr_volume_pyramid(tiled=True) writes -- same values, same outputs, bit for bit (tests/test_parity_gpu.py)
+    FUSED = WITH_CORR and dtype == torch.float16 and WD % 64 == 0 and HT % 8 == 0 and not args.dropin_lookup
+    pyr_t, corr196 = None, None
+    if FUSED:
+        def tile(v, l):
+            h2, w2 = HT >> l, WD >> l
+            return v.view(E, HT, WD, h2 // 4, 4, w2 // 8, 8).permute(0, 1, 2, 3, 5, 4, 6).contiguous().view(E, HT, WD, h2, w2)
+        pyr_t = [tile(pb["pyr"][0], 0), tile(pb["pyr"][1], 1), pb["pyr"][2], pb["pyr"][3]]
+        corr196 = torch.empty(E, 196, HT, WD, dtype=dtype, device=dev)
     stream = torch.cuda.current_stream()
     sp = ctypes.c_void_p(stream.cuda_stream)
     spbox = [sp]
@@ -213,13 +224,20 @@ def run_ours(args, rank, world, dev):
             p2p = None
     drv = sharded.ShardedBA(engine, p2p=p2p)
 
-    def step_resident(ev=None):
-        d["poses"].copy_(pristine_poses); d["disps"].copy_(pristine_disps)
-        if ev: ev[0].record()
+    def lookup_dropin(sp_):
         for l in range(NL):
             v = pb["pyr"][l]
             c_api.check(L.dba_corr_index_forward(ctypes.c_void_p(v.data_ptr()), ctypes.c_void_p(coords_l[l].data_ptr()),
-                                                 ctypes.c_void_p(corr_out[l].data_ptr()), E, HT, WD, v.shape[3], v.shape[4], RADIUS, dcode, spbox[0]), "corr")
+                                                 ctypes.c_void_p(corr_out[l].data_ptr()), E, HT, WD, v.shape[3], v.shape[4], RADIUS, dcode, sp_), "corr")
+
+    def step_resident(ev=None):
+        d["poses"].copy_(pristine_poses); d["disps"].copy_(pristine_disps)
+        if ev: ev[0].record()
+        if FUSED:
+            c_api.check(L.dba_corr_lookup_pyramid(*[ctypes.c_void_p(v.data_ptr()) for v in pyr_t], ctypes.c_void_p(pb["coords"].data_ptr()),
+                                                  ctypes.c_void_p(corr196.data_ptr()), E, HT, WD, 3, dcode, spbox[0]), "corr_lookup_pyramid")
+        else:
+            lookup_dropin(spbox[0])
         if ev: ev[1].record()
         drv.run(d["poses"], d["disps"], d["intrinsics"], d["disps_sens"], d["targets"], d["weights"], d["eta_by_frame"], d["ii"], d["jj"],
                 pb["t0"], pb["t1"], BA_ITERS, LM, EP, pb["bounds"], exchange_disps=(world > 1))
@@ -283,6 +301,13 @@ def run_ours(args, rank, world, dev):
     if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t[0]) / args.steps
     corr_ms = float(t[1])
+    dropin_ms = None
+    if FUSED and world == 1:      # the four drop-in launches on the reference-layout volumes, for comparison (and equality of the results)
+        dropin_ms = _time_ms(lambda: lookup_dropin(sp), iters=min(args.steps, 20), warm=3)
+        ref196 = torch.cat([c.view(E, 49, HT, WD) for c in corr_out], 1)
+        if not torch.equal(ref196, corr196):
+            raise RuntimeError("fused tiled lookup and the drop-in corr_index_forward launches disagree")
+        del ref196
 
     # ---- end to end through the public pybind API from pinned host buffers
     pin = {k: h[k].pin_memory() for k in ("coords", "targets", "weights", "eta", "eta_by_frame", "poses", "disps", "disps_sens", "ii", "jj", "intrinsics")}
@@ -304,7 +329,9 @@ def run_ours(args, rank, world, dev):
             g = {k: pin[k].to(dev, non_blocking=True) for k in pin if k not in ("eta", "eta_by_frame", "coords")}
             eta = (pin["eta"] if world == 1 else pin["eta_by_frame"]).to(dev, non_blocking=True)
         feats = []
-        for l in range(NL):
+        if FUSED:
+            feats.append(be.corr_lookup_pyramid(pyr_t, coords, True))                   # CorrBlock.__call__ through the fused-lookup hook
+        for l in range(0 if FUSED else NL):
             corr, = be.corr_index_forward(pb["pyr"][l], coords / 2 ** l, RADIUS)       # reference call pattern, modules/corr.py:46-48
             feats.append(corr)
         main.wait_stream(copy_stream)
@@ -353,7 +380,7 @@ def run_ours(args, rank, world, dev):
                 for k in stat:
                     if k != "coords":
                         stat[k].copy_(pin[k], non_blocking=True)
-            keep = [be.corr_index_forward(pb["pyr"][l], stat["coords"] / 2 ** l, RADIUS)[0] for l in range(NL)]
+            keep = [be.corr_lookup_pyramid(pyr_t, stat["coords"], True)] if FUSED else [be.corr_index_forward(pb["pyr"][l], stat["coords"] / 2 ** l, RADIUS)[0] for l in range(NL)]
             main.wait_stream(copy_stream)
             if world == 1:
                 dx, dz = be.ba(stat["poses"], stat["disps"], stat["intrinsics"], stat["disps_sens"], stat["targets"], stat["weights"], stat["eta"],
@@ -384,13 +411,14 @@ def run_ours(args, rank, world, dev):
     alg = alg_bytes_corr(E, dtype)
     achieved = alg / (corr_ms * 1e-3) / 1e9 if (WITH_CORR and corr_ms > 0) else 0.0
     traffic = roofline_traffic()
-    launches_per_step = NL + 2 + BA_ITERS * 6        # corr x4, prepare+csr, per GN iter: build, schur x2, chol, backsub, pose_retr
+    launches_per_step = (1 if FUSED else NL) + 2 + BA_ITERS * 6        # corr x4, prepare+csr, per GN iter: build, schur x2, chol, backsub, pose_retr
     Ptot = pb["t1"] - pb["t0"]
     sys_bytes = 8 * (36 * Ptot * Ptot + 6 * Ptot)
     mult = world if SCALING == "weak" else 1
     if CFG_NAME == "metric":
         metric, unit = "BA-update iters/sec (512 edges, 344x64x48)", "iters/s (512-edge equivalents)"
-        workload = "metric: %d edges/GPU x %d GPU(s) over a %d-keyframe window at %dx%d, 4-level r=3 corr_index_forward + ba(itrs=2, lm=1e-4, ep=0.1)" % (EDGES_PER_GPU, world, FRAMES, HT, WD)
+        workload = "metric: %d edges/GPU x %d GPU(s) over a %d-keyframe window at %dx%d, 4-level r=3 correlation lookup (%s) + ba(itrs=2, lm=1e-4, ep=0.1)" % (
+            EDGES_PER_GPU, world, FRAMES, HT, WD, "one fused launch on the tiled volumes of corr_volume_pyramid(tiled=True); the four drop-in corr_index_forward launches are reported under dropin_lookup" if FUSED else "4 x corr_index_forward")
     else:
         metric, unit = "BA-update iters/sec (BASELINE config %s)" % CFG_NAME, "iters/s (one step = %sba(itrs=%d))" % ("4-level corr_index_forward + " if WITH_CORR else "", BA_ITERS)
         workload = "%s: %d edges %s, %d keyframes at %dx%d, %s volumes, %sba(itrs=%d, lm=%g, ep=%g)%s" % (
@@ -408,7 +436,7 @@ def run_ours(args, rank, world, dev):
                          "BA inputs of %.0f MB per rank; L2 not flushed between steps (the reference keeps them resident too)" % (E * HT * WD * 16 / 1e6)},
         "e2e": {"value": mult * 1e3 / e2e_ms, "unit": unit, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "launch_mode": e2e_mode, "eager_ms_per_step": e2e_eager_ms, "h2d_copy_only_ms": copy_only_ms,
-                "api": "droid_backends.corr_index_forward x4 + droid_backends.ba from pinned host buffers (BA inputs copied on a second stream during the lookups); volumes persistent on device"},
+                "api": "droid_backends." + ("corr_lookup_pyramid" if FUSED else "corr_index_forward x4") + " + droid_backends.ba from pinned host buffers (BA inputs copied on a second stream during the lookups); volumes persistent on device"},
         "gpu_launches": launches_per_step * args.steps, "launch_mode": "cuda graph replay" if graph is not None else "eager",
         "clocks": clocks,
         "ba_ms_per_step": ms_step - corr_ms, "ms_per_gn_iteration": (ms_step - corr_ms) / BA_ITERS,
@@ -416,10 +444,11 @@ def run_ours(args, rank, world, dev):
                                   "how": ("every rank reads the %d peer copies inside the solve kernel" % (world - 1)) if p2p is not None else ("NCCL ring all-reduce (2(N-1)/N x bytes per GPU)" if world > 1 else "none")},
     }
     if WITH_CORR:
-        line["roofline"] = {"kernel": "corr_index_fwd_%s_r3_kernel (4 launches/step)" % args.dtype, "bound": "hbm", "achieved": achieved, "peak": peak,
+        kname = "corr_lookup_pyramid_f16_kernel<tiled levels 0-1> (1 launch/step: all 4 levels)" if FUSED else "corr_index_fwd_%s_r3_kernel (4 launches/step)" % args.dtype
+        line["roofline"] = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak,
                             "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
                             "kernel_ms_per_step": corr_ms, "share_of_step": corr_ms / ms_step,
-                            "traffic": (traffic or {}).get("dram_bytes_per_step_" + args.dtype),
+                            "traffic": (traffic or {}).get("dram_bytes_per_step_" + ("fused_tiled_f16" if FUSED else args.dtype)),
                             "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the four launches, profiles/ (captured once per kernel change, not re-measured by this run)"}
     else:
         alg_ba = BA_ITERS * (16 * E * HT * WD + 16 * pb["M"] * HT * WD + 28 * FRAMES)
@@ -427,6 +456,11 @@ def run_ours(args, rank, world, dev):
                             "peak": peak, "unit": "GB/s", "frac": alg_ba / ((ms_step - corr_ms) * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                             "algorithmic_bytes_per_step": alg_ba, "traffic": None,
                             "note": "SURVEY 8d BA bytes (16 E HW + 16 M HW + 28 N per iteration); the step is latency / solve bound, not HBM bound"}
+    if dropin_ms is not None:
+        line["dropin_lookup"] = {"kernel": "corr_index_fwd_f16_r3_kernel (4 launches on reference-layout volumes, the round-1 step)", "kernel_ms_per_step": dropin_ms,
+                                 "achieved": alg / (dropin_ms * 1e-3) / 1e9, "frac": alg / (dropin_ms * 1e-3) / 1e9 / peak, "unit": "GB/s",
+                                 "step_ms_with_dropin_lookup": ms_step - corr_ms + dropin_ms, "value_with_dropin_lookup": mult * 1e3 / (ms_step - corr_ms + dropin_ms),
+                                 "traffic": (traffic or {}).get("dram_bytes_per_step_" + args.dtype), "outputs": "bit-identical to the fused lookup (checked in this run)"}
     if world == 1 and not args.no_extras:
         extras = secondary_kernels(E, dev, ms_step, L, be)
         line["update_operator"] = extras.pop("update_operator")

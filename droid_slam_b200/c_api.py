@@ -6,7 +6,7 @@ _LIB = None
 
 SYMBOLS = [
     "dba_last_error", "dba_version", "dba_set_l2_fetch_granularity", "dba_get_l2_fetch_granularity",
-    "dba_corr_index_forward", "dba_corr_index_backward", "dba_corr_volume_pyramid", "dba_corr_volume_supported", "dba_altcorr_forward", "dba_altcorr_backward",
+    "dba_corr_index_forward", "dba_corr_index_backward", "dba_corr_volume_pyramid", "dba_corr_volume_pyramid_tiled", "dba_corr_lookup_pyramid", "dba_corr_volume_supported", "dba_altcorr_forward", "dba_altcorr_backward",
     "dba_projmap", "dba_reproject", "dba_frame_distance", "dba_depth_filter", "dba_iproj",
     "dba_ba_workspace_bytes", "dba_ba_system_offset", "dba_ba_system_bytes",
     "dba_ba_prepare", "dba_ba_build", "dba_ba_solve", "dba_ba", "dba_ba_read_info", "dba_ba_p2p_signal",
@@ -56,6 +56,8 @@ def load():
     L.dba_corr_index_forward.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
     L.dba_corr_index_backward.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, ci, vp]
     L.dba_corr_volume_pyramid.argtypes = [vp] * 8 + [ci] * 7 + [vp]
+    L.dba_corr_volume_pyramid_tiled.argtypes = [vp] * 8 + [ci] * 7 + [vp]
+    L.dba_corr_lookup_pyramid.argtypes = [vp] * 6 + [ci] * 5 + [vp]
     L.dba_altcorr_forward.argtypes = [vp, vp, vp, vp, vp, vp] + [ci] * 11 + [vp]
     L.dba_altcorr_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp] + [ci] * 11 + [vp]
     L.dba_projmap.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp]

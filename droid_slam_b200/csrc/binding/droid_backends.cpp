@@ -247,7 +247,7 @@ std::vector<torch::Tensor> altcorr_backward(torch::Tensor fmap1, torch::Tensor f
 
 // extension beyond the reference's nine callables: CorrBlock.__init__ in one tensor-core kernel
 // (reference droid_slam/modules/corr.py:24-38,63-71).  fmap1/fmap2 [N,128,ht,wd] f16, ii/jj [E] -> 4 pyramid levels.
-std::vector<torch::Tensor> corr_volume_pyramid(torch::Tensor fmap1, torch::Tensor fmap2, torch::Tensor ii, torch::Tensor jj) {
+std::vector<torch::Tensor> corr_volume_pyramid(torch::Tensor fmap1, torch::Tensor fmap2, torch::Tensor ii, torch::Tensor jj, bool tiled) {
   CHECK_INPUT(fmap1); CHECK_INPUT(fmap2); CHECK_INPUT(ii); CHECK_INPUT(jj); CHECK_I64(ii); CHECK_I64(jj);
   TORCH_CHECK(fmap1.dim() == 4 && fmap2.dim() == 4, "fmaps must be [N,C,ht,wd]");
   TORCH_CHECK(fmap1.scalar_type() == torch::kFloat16 && fmap2.scalar_type() == torch::kFloat16, "corr_volume_pyramid: float16 feature maps expected");
@@ -257,9 +257,26 @@ std::vector<torch::Tensor> corr_volume_pyramid(torch::Tensor fmap1, torch::Tenso
   TORCH_CHECK(jj.size(0) == E, "ii and jj must have the same length");
   std::vector<torch::Tensor> out;
   for (int l = 0; l < 4; l++) out.push_back(torch::empty({E, ht, wd, ht >> l, wd >> l}, fmap1.options()));
-  check_status(dba_corr_volume_pyramid(fmap1.data_ptr(), fmap2.data_ptr(), ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(), out[0].data_ptr(),
-                                       out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), E, (int)fmap1.size(0), (int)fmap2.size(0), C, ht, wd,
+  check_status((tiled ? dba_corr_volume_pyramid_tiled : dba_corr_volume_pyramid)(fmap1.data_ptr(), fmap2.data_ptr(), ii.data_ptr<int64_t>(), jj.data_ptr<int64_t>(),
+                                       out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), E, (int)fmap1.size(0), (int)fmap2.size(0), C, ht, wd,
                                        DBA_F16, cur_stream()), "corr_volume_pyramid");
+  return out;
+}
+
+// extension: CorrBlock.__call__ (reference modules/corr.py:40-50) in one launch.  pyramid = 4 f16 tensors [E,h1,w1,h1/2^l,w1/2^l] (reference
+// layout, or levels 0-1 tiled when `tiled`), coords [E,2,h1,w1] f32 at level-0 scale -> [E,196,h1,w1] = cat over levels of corr_index_forward
+torch::Tensor corr_lookup_pyramid(std::vector<torch::Tensor> pyramid, torch::Tensor coords, bool tiled) {
+  TORCH_CHECK(pyramid.size() == 4, "corr_lookup_pyramid: 4 pyramid levels expected");
+  CHECK_INPUT(coords); CHECK_F32(coords);
+  for (auto& v : pyramid) { CHECK_INPUT(v); TORCH_CHECK(v.scalar_type() == torch::kFloat16 && v.dim() == 5, "pyramid levels must be f16 [E,h1,w1,h2,w2]"); }
+  const int n = (int)pyramid[0].size(0), h1 = (int)pyramid[0].size(1), w1 = (int)pyramid[0].size(2);
+  TORCH_CHECK(coords.dim() == 4 && coords.size(0) == n && coords.size(1) == 2 && coords.size(2) == h1 && coords.size(3) == w1, "coords must be [E,2,h1,w1]");
+  for (int l = 0; l < 4; l++)
+    TORCH_CHECK(pyramid[l].size(0) == n && pyramid[l].size(1) == h1 && pyramid[l].size(2) == w1 && pyramid[l].size(3) == (h1 >> l) && pyramid[l].size(4) == (w1 >> l), "pyramid level ", l, " has the wrong shape");
+  c10::cuda::CUDAGuard guard(coords.device());
+  auto out = torch::empty({n, 196, h1, w1}, pyramid[0].options());
+  check_status(dba_corr_lookup_pyramid(pyramid[0].data_ptr(), pyramid[1].data_ptr(), pyramid[2].data_ptr(), pyramid[3].data_ptr(), coords.data_ptr<float>(), out.data_ptr(),
+                                       n, h1, w1, tiled ? 3 : 0, DBA_F16, cur_stream()), "corr_lookup_pyramid");
   return out;
 }
 
@@ -369,7 +386,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("altcorr_backward", &altcorr_backward, "ALTCORR backward");
   m.def("corr_index_forward", &corr_index_forward, "INDEX forward");
   m.def("corr_index_backward", &corr_index_backward, "INDEX backward");
-  m.def("corr_volume_pyramid", &corr_volume_pyramid, "all-pairs correlation + 4-level pyramid (tcgen05), B200 extension");
+  m.def("corr_volume_pyramid", &corr_volume_pyramid, "all-pairs correlation + 4-level pyramid (tcgen05), B200 extension", pybind11::arg("fmap1"), pybind11::arg("fmap2"),
+        pybind11::arg("ii"), pybind11::arg("jj"), pybind11::arg("tiled") = false);
+  m.def("corr_lookup_pyramid", &corr_lookup_pyramid, "4-level radius-3 lookup in one launch -> [E,196,H,W], B200 extension", pybind11::arg("pyramid"), pybind11::arg("coords"),
+        pybind11::arg("tiled") = false);
   m.def("corr_volume_supported", [](int dim, int ht, int wd) { return dba_corr_volume_supported(dim, ht, wd, DBA_F16) != 0; }, "does corr_volume_pyramid have a kernel for f16 [.,dim,ht,wd] feature maps");
   m.def("reproject", &reproject, "fused pops.projective_transform(jacobian=False), B200 extension");
   m.def("update_forward", &update_forward, "update operator (ConvGRU + heads + GraphAgg) on tcgen05, B200 extension");

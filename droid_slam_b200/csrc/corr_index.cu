@@ -192,18 +192,20 @@ __device__ __forceinline__ void align_row_f16(const uint4& A, const uint4& B, in
   t[0] = w0; t[1] = w1; t[2] = w2; t[3] = w3; t4 = 0;
 }
 
-__global__ void __launch_bounds__(128) corr_index_fwd_f16_r3_kernel(const __half* __restrict__ vol, const float* __restrict__ coords,
-                                                                    __half* __restrict__ out, long long total, int hw1, int h2, int w2) {
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  const int n = (int)(p / hw1);
-  const int pin = (int)(p - (long long)n * hw1);
-  const float x0 = coords[((size_t)n * 2 + 0) * hw1 + pin];
-  const float y0 = coords[((size_t)n * 2 + 1) * hw1 + pin];
-  const __half* plane = vol + (size_t)p * h2 * w2;
-  __half* out_px = out + (size_t)n * 49 * hw1 + pin;
-  if (!(isfinite(x0) && isfinite(y0))) {   // exact skip semantics for NaN/inf coordinates
-    corr_pixel_generic<__half>(plane, out_px, (size_t)hw1, x0, y0, h2, w2, 3);
+// one pixel, one level, f16, radius 3: out_px[(i*7+j) * out_stride] for the 49 taps.  TILED: the plane is stored as 4x8-element
+// tiles ([h2/4][w2/8][4][8], one 64-byte DRAM atom per tile, written by corr_volume_pyramid's tiled mode): the 8x8 window then
+// touches 5.2 atoms on average instead of 8-10 (a 16-byte window row at arbitrary alignment costs a whole atom in the row-major
+// plane); the arithmetic and therefore every output bit is the same.
+template <bool TILED>
+__device__ __forceinline__ void corr_pixel_f16_r3(const __half* __restrict__ plane, __half* __restrict__ out_px, size_t out_stride,
+                                                  float x0, float y0, int h2, int w2) {
+  if (!(isfinite(x0) && isfinite(y0))) {   // exact skip semantics for NaN/inf coordinates (nothing is in bounds -> zeros)
+    if (TILED) {
+#pragma unroll 1
+      for (int k = 0; k < 49; k++) out_px[(size_t)k * out_stride] = __float2half_rn(0.f);
+    } else {
+      corr_pixel_generic<__half>(plane, out_px, out_stride, x0, y0, h2, w2, 3);
+    }
     return;
   }
   const float fxf = floorf(x0), fyf = floorf(y0);
@@ -212,16 +214,17 @@ __global__ void __launch_bounds__(128) corr_index_fwd_f16_r3_kernel(const __half
   const int a0 = x1s & ~7;
   const int o = x1s - a0;
   const bool okA = (unsigned)a0 < (unsigned)w2, okB = (unsigned)(a0 + 8) < (unsigned)w2;
+  const int tpr = w2 >> 3;                                   // tiles per tile row
 
   uint4 A[8], B[8];
 #pragma unroll
   for (int b = 0; b < 8; b++) {
     const int y1 = y1s + b;
     const bool rowok = (unsigned)y1 < (unsigned)h2;
-    const __half* row = plane + (size_t)y1 * w2 + a0;
+    const __half* row = TILED ? plane + ((size_t)(y1 >> 2) * tpr + (a0 >> 3)) * 32 + (y1 & 3) * 8 : plane + (size_t)y1 * w2 + a0;
     A[b] = make_uint4(0, 0, 0, 0); B[b] = make_uint4(0, 0, 0, 0);
     if (rowok && okA) A[b] = ldg_nc_v4(row);
-    if (rowok && okB) B[b] = ldg_nc_v4(row + 8);
+    if (rowok && okB) B[b] = ldg_nc_v4(row + (TILED ? 32 : 8));
   }
   const __half2 w00 = __half2half2(__float2half_rn((1.0f - dx) * (1.0f - dy)));
   const __half2 w01 = __half2half2(__float2half_rn((1.0f - dx) * dy));
@@ -244,12 +247,46 @@ __global__ void __launch_bounds__(128) corr_index_fwd_f16_r3_kernel(const __half
       t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(ca[k]), w01));               // tap (i  , j+1)
       t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(ps[k]), w10));               // tap (i+1, j  )
       t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(cs[k]), w11));               // tap (i+1, j+1)
-      out_px[(size_t)((2 * k) * 7 + j) * hw1] = __low2half(t);
-      if (k < 3) out_px[(size_t)((2 * k + 1) * 7 + j) * hw1] = __high2half(t);
+      out_px[(size_t)((2 * k) * 7 + j) * out_stride] = __low2half(t);
+      if (k < 3) out_px[(size_t)((2 * k + 1) * 7 + j) * out_stride] = __high2half(t);
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) { pa[k] = ca[k]; ps[k] = cs[k]; }
   }
+}
+
+__global__ void __launch_bounds__(128) corr_index_fwd_f16_r3_kernel(const __half* __restrict__ vol, const float* __restrict__ coords,
+                                                                    __half* __restrict__ out, long long total, int hw1, int h2, int w2) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int n = (int)(p / hw1);
+  const int pin = (int)(p - (long long)n * hw1);
+  const float x0 = coords[((size_t)n * 2 + 0) * hw1 + pin];
+  const float y0 = coords[((size_t)n * 2 + 1) * hw1 + pin];
+  corr_pixel_f16_r3<false>(vol + (size_t)p * h2 * w2, out + (size_t)n * 49 * hw1 + pin, (size_t)hw1, x0, y0, h2, w2);
+}
+
+// CorrBlock.__call__ (reference modules/corr.py:40-50) in ONE launch: all four pyramid levels of a pixel by one thread -- the
+// coordinates are read once, the level-l lookup uses coords / 2^l (exact in fp32, like the reference's `coords/2**i`), and the four
+// [49,H,W] results land directly in the concatenated [E,196,H,W] tensor the update operator consumes (the reference allocates four
+// tensors and copies them with torch.cat).  tiled_levels: bit l set = level l is stored in the 4x8-tile layout.
+template <int TILED_MASK>
+__global__ void __launch_bounds__(128) corr_lookup_pyramid_f16_kernel(const __half* __restrict__ v0, const __half* __restrict__ v1,
+                                                                      const __half* __restrict__ v2, const __half* __restrict__ v3,
+                                                                      const float* __restrict__ coords, __half* __restrict__ out,
+                                                                      long long total, int hw1, int h1, int w1) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int n = (int)(p / hw1);
+  const int pin = (int)(p - (long long)n * hw1);
+  const float x0 = coords[((size_t)n * 2 + 0) * hw1 + pin];
+  const float y0 = coords[((size_t)n * 2 + 1) * hw1 + pin];
+  __half* o = out + (size_t)n * 196 * hw1 + pin;
+  // coarse levels first: their planes are small and their loads return while the level-0 window (the expensive one) is being issued
+  corr_pixel_f16_r3<(TILED_MASK & 8) != 0>(v3 + (size_t)p * (h1 >> 3) * (w1 >> 3), o + (size_t)147 * hw1, (size_t)hw1, x0 * 0.125f, y0 * 0.125f, h1 >> 3, w1 >> 3);
+  corr_pixel_f16_r3<(TILED_MASK & 4) != 0>(v2 + (size_t)p * (h1 >> 2) * (w1 >> 2), o + (size_t)98 * hw1, (size_t)hw1, x0 * 0.25f, y0 * 0.25f, h1 >> 2, w1 >> 2);
+  corr_pixel_f16_r3<(TILED_MASK & 2) != 0>(v1 + (size_t)p * (h1 >> 1) * (w1 >> 1), o + (size_t)49 * hw1, (size_t)hw1, x0 * 0.5f, y0 * 0.5f, h1 >> 1, w1 >> 1);
+  corr_pixel_f16_r3<(TILED_MASK & 1) != 0>(v0 + (size_t)p * h1 * w1, o, (size_t)hw1, x0, y0, h1, w1);
 }
 
 __global__ void __launch_bounds__(128) corr_index_fwd_f32_r3_kernel(const float* __restrict__ vol, const float* __restrict__ coords,
@@ -390,3 +427,27 @@ extern "C" int dba_corr_index_backward(const float* coords, const void* corr_gra
     default: return launch_bwd<__nv_bfloat16>(coords, corr_grad, volume_grad, total, hw1, h2, w2, radius, st);
   }
 }
+
+// fused 4-level lookup (f16, radius 3): out [n,196,h1,w1] = cat over levels of corr_index_forward(volume_l, coords / 2^l).
+// tiled_mask bit l: level l is in the 4x8-tile layout of dba_corr_volume_pyramid(..., tiled = 1) (levels 0 and 1 there).
+extern "C" int dba_corr_lookup_pyramid(const void* v0, const void* v1, const void* v2, const void* v3, const float* coords, void* out,
+                                       int n, int h1, int w1, int tiled_mask, int dtype, dba_stream_t stream) {
+  DBA_CHECK_ARG(n >= 0 && h1 > 0 && w1 > 0, "bad extents");
+  DBA_CHECK_ARG(dtype == DBA_F16, "corr_lookup_pyramid: f16 volumes (the live system's autocast dtype) only; use corr_index_forward per level otherwise");
+  DBA_CHECK_ARG(h1 % 8 == 0 && w1 % 64 == 0, "corr_lookup_pyramid: needs w1 % 64 == 0 (every level's rows are whole 16-byte chunks) and h1 % 8 == 0");
+  DBA_CHECK_ARG(tiled_mask == 0 || (tiled_mask == 3 && h1 % 8 == 0), "tiled_mask must be 0 or 3 (levels 0 and 1 tiled)");
+  const long long total = (long long)n * h1 * w1;
+  if (total == 0) return DBA_OK;
+  DBA_CHECK_ARG(v0 && v1 && v2 && v3 && coords && out, "null pointer");
+  DBA_CHECK_ARG(((((uintptr_t)v0) | ((uintptr_t)v1) | ((uintptr_t)v2) | ((uintptr_t)v3)) & 15) == 0, "volumes must be 16-byte aligned");
+  DBA_CHECK_ARG((total + 127) / 128 < 0x7fffffffLL, "too many pixels for one launch");
+  const unsigned blocks = (unsigned)((total + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tiled_mask == 3)
+    corr_lookup_pyramid_f16_kernel<3><<<blocks, 128, 0, st>>>((const __half*)v0, (const __half*)v1, (const __half*)v2, (const __half*)v3, coords, (__half*)out, total, h1 * w1, h1, w1);
+  else
+    corr_lookup_pyramid_f16_kernel<0><<<blocks, 128, 0, st>>>((const __half*)v0, (const __half*)v1, (const __half*)v2, (const __half*)v3, coords, (__half*)out, total, h1 * w1, h1, w1);
+  DBA_CHECK_LAUNCH("corr_lookup_pyramid");
+  return DBA_OK;
+}
+

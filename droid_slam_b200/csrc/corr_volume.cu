@@ -69,6 +69,7 @@ struct CvParams {
   const int64_t* ii; const int64_t* jj;
   __half* out0; __half* out1; __half* out2; __half* out3;
   int HW, wd, n_chunks;
+  int tiled;     // levels 0 and 1 in 4x8-element tiles ([h/4][w/8][4][8], one 64-byte DRAM atom per tile) for corr_lookup_pyramid
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -182,14 +183,31 @@ __global__ void __launch_bounds__(kCvThreads, 1) corr_volume_pyramid_kernel(cons
           wb[k] = pack_h2(__uint_as_float(rb[2 * k]) * sc, __uint_as_float(rb[2 * k + 1]) * sc);
           l1f[rp][k] = ((__uint_as_float(ra[2 * k]) + __uint_as_float(ra[2 * k + 1])) + (__uint_as_float(rb[2 * k]) + __uint_as_float(rb[2 * k + 1]))) * (0.25f * sc);
         }
-        // level 0: 32 halves = 64 contiguous bytes per image row, as 256-bit stores (one full 32-byte sector each)
-        st_v8(o0 + (size_t)c * kCvN + (2 * rp) * 64, wa);      st_v8(o0 + (size_t)c * kCvN + (2 * rp) * 64 + 16, wa + 8);
-        st_v8(o0 + (size_t)c * kCvN + (2 * rp + 1) * 64, wb);  st_v8(o0 + (size_t)c * kCvN + (2 * rp + 1) * 64 + 16, wb + 8);
-        // level 1 row 2c + rp: 16 halves = 32 bytes
-        uint32_t w1[8];
+        if (!p.tiled) {
+          // level 0: 32 halves = 64 contiguous bytes per image row, as 256-bit stores (one full 32-byte sector each)
+          st_v8(o0 + (size_t)c * kCvN + (2 * rp) * 64, wa);      st_v8(o0 + (size_t)c * kCvN + (2 * rp) * 64 + 16, wa + 8);
+          st_v8(o0 + (size_t)c * kCvN + (2 * rp + 1) * 64, wb);  st_v8(o0 + (size_t)c * kCvN + (2 * rp + 1) * 64 + 16, wb + 8);
+          // level 1 row 2c + rp: 16 halves = 32 bytes
+          uint32_t w1[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) w1[k] = pack_h2(l1f[rp][2 * k], l1f[rp][2 * k + 1]);
-        st_v8(o1 + (size_t)(2 * c + rp) * (wd / 2), w1);
+          for (int k = 0; k < 8; k++) w1[k] = pack_h2(l1f[rp][2 * k], l1f[rp][2 * k + 1]);
+          st_v8(o1 + (size_t)(2 * c + rp) * (wd / 2), w1);
+        } else {
+          // tiled level 0: chunk c = tile row c; this thread's 32 columns = tiles 4*half .. 4*half+3; rows 2rp, 2rp+1 of a tile are
+          // adjacent 16-byte pieces -> one 32-byte sector per tile
+          __half* t0 = p.out0 + ((size_t)e * p.HW + m) * (size_t)p.HW + ((size_t)c * 8 + 4 * half) * 32 + (2 * rp) * 8;
+#pragma unroll
+          for (int t = 0; t < 4; t++) {
+            const uint32_t w8[8] = {wa[4 * t], wa[4 * t + 1], wa[4 * t + 2], wa[4 * t + 3], wb[4 * t], wb[4 * t + 1], wb[4 * t + 2], wb[4 * t + 3]};
+            st_v8(t0 + t * 32, w8);
+          }
+          // tiled level 1 (24 x 32 plane, 4 tiles per tile row): row 2c+rp -> tile row c/2, row 2(c&1)+rp inside; tiles 2*half, 2*half+1
+          __half* t1 = p.out1 + ((size_t)e * p.HW + m) * (size_t)(p.HW / 4) + ((size_t)(c >> 1) * 4 + 2 * half) * 32 + (2 * (c & 1) + rp) * 8;
+#pragma unroll
+          for (int t = 0; t < 2; t++)
+            *reinterpret_cast<uint4*>(t1 + t * 32) = make_uint4(pack_h2(l1f[rp][8 * t], l1f[rp][8 * t + 1]), pack_h2(l1f[rp][8 * t + 2], l1f[rp][8 * t + 3]),
+                                                               pack_h2(l1f[rp][8 * t + 4], l1f[rp][8 * t + 5]), pack_h2(l1f[rp][8 * t + 6], l1f[rp][8 * t + 7]));
+        }
       }
       // accumulator drained: hand the TMEM stage back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -252,9 +270,9 @@ extern "C" int dba_corr_volume_supported(int channels, int ht, int wd, int dtype
   return (dtype == DBA_F16 && channels == 128 && wd == 64 && ht > 0 && ht % 8 == 0) ? 1 : 0;
 }
 
-extern "C" int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj, void* out0, void* out1,
-                                       void* out2, void* out3, int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd,
-                                       int dtype, dba_stream_t stream) {
+static int corr_volume_launch(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj, void* out0, void* out1,
+                              void* out2, void* out3, int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd,
+                              int dtype, int tiled, dba_stream_t stream) {
   DBA_CHECK_ARG(n_edges >= 0 && n_frames1 > 0 && n_frames2 > 0, "bad extents");
   DBA_CHECK_ARG(dtype == DBA_F16, "corr_volume_pyramid: only f16 features (the live system's autocast dtype) are implemented");
   DBA_CHECK_ARG(channels == 128, "corr_volume_pyramid: 128 feature channels expected (reference fnet)");
@@ -271,9 +289,24 @@ extern "C" int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, con
   if (!attr) { DBA_CHECK_CUDA(cudaFuncSetAttribute(corr_volume_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem), "corr_volume smem attr"); attr = true; }
   CvParams p;
   p.ii = ii; p.jj = jj; p.out0 = (__half*)out0; p.out1 = (__half*)out1; p.out2 = (__half*)out2; p.out3 = (__half*)out3;
-  p.HW = HW; p.wd = wd; p.n_chunks = HW / kCvN;
+  p.HW = HW; p.wd = wd; p.n_chunks = HW / kCvN; p.tiled = tiled;
   dim3 grid(HW / kCvM, n_edges);
   corr_volume_pyramid_kernel<<<grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(tmA, tmB, p);
   DBA_CHECK_LAUNCH("corr_volume_pyramid");
   return DBA_OK;
 }
+
+extern "C" int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj, void* out0, void* out1,
+                                       void* out2, void* out3, int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd,
+                                       int dtype, dba_stream_t stream) {
+  return corr_volume_launch(fmap1, fmap2, ii, jj, out0, out1, out2, out3, n_edges, n_frames1, n_frames2, channels, ht, wd, dtype, 0, stream);
+}
+
+// same volumes, levels 0 and 1 stored as 4x8-element tiles per plane (private layout of dba_corr_lookup_pyramid with tiled_mask = 3;
+// levels 2 and 3 keep the reference layout).  The tensors keep their [E,ht,wd,h2,w2] shapes and sizes; only the order inside a plane differs.
+extern "C" int dba_corr_volume_pyramid_tiled(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj, void* out0, void* out1,
+                                             void* out2, void* out3, int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd,
+                                             int dtype, dba_stream_t stream) {
+  return corr_volume_launch(fmap1, fmap2, ii, jj, out0, out1, out2, out3, n_edges, n_frames1, n_frames2, channels, ht, wd, dtype, 1, stream);
+}
+

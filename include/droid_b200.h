@@ -62,6 +62,18 @@ int dba_corr_volume_pyramid(const void* fmap1, const void* fmap2, const int64_t*
                             void* out0, void* out1, void* out2, void* out3,
                             int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd, int dtype, dba_stream_t stream);
 
+/* private-layout variant: levels 0 and 1 of every plane stored as 4x8-element tiles ([h2/4][w2/8][4][8] f16 = one 64-byte DRAM atom per
+ * tile) for dba_corr_lookup_pyramid(tiled_mask = 3); levels 2, 3 and all tensor shapes are unchanged.  NOT readable by
+ * dba_corr_index_forward / the reference's CorrBlock.__call__. */
+int dba_corr_volume_pyramid_tiled(const void* fmap1, const void* fmap2, const int64_t* ii, const int64_t* jj,
+                                  void* out0, void* out1, void* out2, void* out3,
+                                  int n_edges, int n_frames1, int n_frames2, int channels, int ht, int wd, int dtype, dba_stream_t stream);
+/* CorrBlock.__call__ (reference droid_slam/modules/corr.py:40-50) in one launch: out [n,196,h1,w1] = concatenation over the four levels
+ * of corr_index_forward(volume_l, coords / 2^l, 3) -- bit-identical values; coords [n,2,h1,w1] f32 at level-0 scale are read once.
+ * f16 volumes, h1 % 8 == 0, w1 % 64 == 0.  tiled_mask: 0 = reference layout, 3 = levels 0 and 1 in the tiled layout above. */
+int dba_corr_lookup_pyramid(const void* v0, const void* v1, const void* v2, const void* v3, const float* coords, void* out,
+                            int n, int h1, int w1, int tiled_mask, int dtype, dba_stream_t stream);
+
 /* ---- on-the-fly correlation ---------------------------------------------------------------------
  * replaces altcorr_cuda_forward / altcorr_cuda_backward (reference src/altcorr_kernel.cu:132-225, bound at
  * src/droid.cpp:198-226).

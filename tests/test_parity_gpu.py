@@ -349,6 +349,31 @@ def test_tensor_core_volume_plus_lookup_matches_oracle_corrblock(backends):
     assert rel_err(alt.float(), got.float(), floor=float(ref.abs().max())) < 1e-2      # two fp16 pipelines with different rounding points
 
 
+@pytest.mark.parametrize("ht", [16, 48])
+def test_fused_pyramid_lookup_and_tiled_volumes_are_bit_identical(backends, ht):
+    """corr_lookup_pyramid (one launch, [E,196,H,W]) == cat of the four corr_index_forward results, for the reference layout and for
+    the tiled private layout written by corr_volume_pyramid(tiled=True); the tiled planes are a pure re-ordering of the same values"""
+    g = torch.Generator().manual_seed(51 + ht)
+    N, C, wd, E = 5, 128, 64, 7
+    fmaps = torch.randn(N, C, ht, wd, generator=g).half().to(dev)
+    ii = torch.randint(0, N, (E,), generator=g).to(dev); jj = torch.randint(0, N, (E,), generator=g).to(dev)
+    coords = torch.stack([torch.rand(E, ht, wd, generator=g) * (wd + 10) - 5, torch.rand(E, ht, wd, generator=g) * (ht + 10) - 5], dim=1)
+    coords[0, :, 0, 0] = torch.tensor([float("inf"), 3.0]); coords[0, :, 0, 1] = torch.tensor([2.0, float("nan")]); coords[1, :, 1, 1] = torch.tensor([-50.0, 1e6])
+    coords = coords.contiguous().to(dev)
+    pyr = backends.corr_volume_pyramid(fmaps, fmaps, ii, jj)
+    per_level = torch.cat([backends.corr_index_forward(pyr[l], (coords / 2 ** l).contiguous(), 3)[0].view(E, 49, ht, wd) for l in range(4)], dim=1)
+    fused = backends.corr_lookup_pyramid(pyr, coords)
+    assert fused.shape == (E, 196, ht, wd)
+    assert_bit_identical(fused, per_level, "fused lookup, reference layout")
+    tpyr = backends.corr_volume_pyramid(fmaps, fmaps, ii, jj, True)
+    assert torch.equal(tpyr[2], pyr[2]) and torch.equal(tpyr[3], pyr[3])
+    for l in (0, 1):                                   # [h2/4][w2/8][4][8] tiles -> [h2][w2]
+        h2, w2 = ht >> l, wd >> l
+        untiled = tpyr[l].view(E, ht, wd, h2 // 4, w2 // 8, 4, 8).permute(0, 1, 2, 3, 5, 4, 6).reshape(E, ht, wd, h2, w2)
+        assert_bit_identical(untiled, pyr[l], "tiled level %d" % l)
+    assert_bit_identical(backends.corr_lookup_pyramid(tpyr, coords, True), per_level, "fused lookup, tiled layout")
+
+
 def test_fused_reproject_matches_projective_transform_restatement(backends):
     """A5: DepthVideo.reproject / pops.projective_transform(jacobian=False) in one kernel, incl. per-frame intrinsics, stereo edges
     and the MIN_DEPTH = 0.2 / Z < 0.1 -> 1 quirk (Q3)"""

@@ -89,3 +89,8 @@ def test_corr_volume_hook_replaces_the_constructor_only(backends):
     assert out.shape == (1, 3, 4 * 49, 16, 64)
     with pytest.raises(RuntimeError):
         mod.CorrBlock(f1.float(), f2.float())                  # no silent library fallback for shapes / dtypes without a kernel
+    # fused mode: tiled volumes + one-launch lookup give the same bits as the reference-layout path
+    mod2 = types.SimpleNamespace(CorrBlock=type("CorrBlock", (_RefShapedCorrBlock,), {}))
+    install_corr_volume_hook(mod2, fused_lookup=True)
+    out2 = mod2.CorrBlock(f1, f2)(coords.to(dev))
+    assert torch.equal(out2, out)
