@@ -7,7 +7,7 @@ _LIB = None
 SYMBOLS = [
     "dba_last_error", "dba_version", "dba_set_l2_fetch_granularity", "dba_get_l2_fetch_granularity",
     "dba_corr_index_forward", "dba_corr_index_backward", "dba_corr_volume_pyramid", "dba_corr_volume_pyramid_tiled", "dba_corr_lookup_pyramid", "dba_corr_volume_supported", "dba_altcorr_forward", "dba_altcorr_backward",
-    "dba_projmap", "dba_reproject", "dba_frame_distance", "dba_depth_filter", "dba_iproj",
+    "dba_projmap", "dba_reproject", "dba_cvx_upsample", "dba_frame_distance", "dba_depth_filter", "dba_iproj",
     "dba_ba_workspace_bytes", "dba_ba_system_offset", "dba_ba_system_bytes",
     "dba_ba_prepare", "dba_ba_build", "dba_ba_solve", "dba_ba", "dba_ba_read_info", "dba_ba_p2p_signal",
     "dba_solve_workspace_bytes", "dba_solve_spd",

@@ -373,6 +373,19 @@ torch::Tensor conv_nhwc(torch::Tensor src0, c10::optional<torch::Tensor> src1, t
   return out;
 }
 
+// extension: cvx_upsample of inverse depths (reference droid_net.py:21-42 via DepthVideo.upsample, depth_video.py:155-159).
+// disps [n,ht,wd] f32, mask [n,576,ht,wd] f16/f32 -> [n,8ht,8wd] f32
+torch::Tensor cvx_upsample(torch::Tensor disps, torch::Tensor mask) {
+  CHECK_INPUT(disps); CHECK_INPUT(mask); CHECK_F32(disps);
+  TORCH_CHECK(disps.dim() == 3 && mask.dim() == 4 && mask.size(0) == disps.size(0) && mask.size(1) == 576 && mask.size(2) == disps.size(1) && mask.size(3) == disps.size(2),
+              "disps [n,ht,wd], mask [n,576,ht,wd]");
+  c10::cuda::CUDAGuard guard(disps.device());
+  const int n = (int)disps.size(0), ht = (int)disps.size(1), wd = (int)disps.size(2);
+  auto out = torch::empty({n, 8 * ht, 8 * wd}, disps.options());
+  check_status(dba_cvx_upsample(disps.data_ptr<float>(), mask.data_ptr(), out.data_ptr<float>(), n, ht, wd, dtype_code(mask, "cvx_upsample"), cur_stream()), "cvx_upsample");
+  return out;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native droid_backends (drop-in for princeton-vl/DROID-SLAM src/droid.cpp)";
   // bundle adjustment kernels
@@ -394,5 +407,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("reproject", &reproject, "fused pops.projective_transform(jacobian=False), B200 extension");
   m.def("update_forward", &update_forward, "update operator (ConvGRU + heads + GraphAgg) on tcgen05, B200 extension");
   m.def("conv_nhwc", &conv_nhwc, "channels-last 1x1/3x3 convolution on tcgen05, B200 extension");
+  m.def("cvx_upsample", &cvx_upsample, "convex upsampling of inverse depth maps (droid_net.cvx_upsample, dim = 1), B200 extension");
   m.def("_b200_native", []() { return true; });
 }

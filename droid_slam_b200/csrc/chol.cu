@@ -186,37 +186,56 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
   {
     const size_t total = (size_t)(nt + 1) * kT * ld;
     const size_t nn = (size_t)n * n;
-    for (size_t idx = (size_t)cta * kCholThreads + tid; idx < total; idx += (size_t)ncta * kCholThreads) {
-      const int r = (int)(idx / ld), c = (int)(idx - (size_t)r * ld);
-      double v = 0.0;
-      size_t src = (size_t)-1;                          // element of the [n*n | n] system feeding this entry
-      if (r < nt * kT) {
-        if (r < n && c < n) {
-          if (c <= r) src = (size_t)r * n + c;
-          else if ((r >> 5) == (c >> 5)) src = (size_t)c * n + r;     // diagonal tiles are kept fully symmetric
-        } else if (r == c) v = 1.0;
-      } else if (r == nt * kT && c < n) src = nn + c;
-      if (src != (size_t)-1) {
-        if (world > 1) {
-          // all peer loads are issued before the first add (the NVLink round trips overlap), then summed in fixed rank order:
-          // every rank computes the identical sum
-          double t[8];
+    const size_t stride = (size_t)ncta * kCholThreads;
+    constexpr int kU = 4;                               // elements per thread in flight: with peers, kU x world NVLink loads overlap their ~2 us round trips
+    for (size_t base = (size_t)cta * kCholThreads + tid; base < total; base += kU * stride) {
+      size_t srcs[kU];
+      double vals[kU];
+      double t[kU][8];
 #pragma unroll
-          for (int q = 0; q < 8; q++) {
-            t[q] = 0.0;
-            if (q < world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t[q]) : "l"(p.peers.sys[q] + src) : "memory");
-          }
+      for (int u = 0; u < kU; u++) {
+        const size_t idx = base + u * stride;
+        srcs[u] = (size_t)-1; vals[u] = 0.0;
+        if (idx < total) {
+          const int r = (int)(idx / ld), c = (int)(idx - (size_t)r * ld);
+          if (r < nt * kT) {
+            if (r < n && c < n) {
+              if (c <= r) srcs[u] = (size_t)r * n + c;
+              else if ((r >> 5) == (c >> 5)) srcs[u] = (size_t)c * n + r;     // diagonal tiles are kept fully symmetric
+            } else if (r == c) vals[u] = 1.0;
+          } else if (r == nt * kT && c < n) srcs[u] = nn + c;
+        }
+        if (srcs[u] != (size_t)-1) {                      // element of the [n*n | n] system feeding this entry
+          if (world > 1) {
 #pragma unroll
-          for (int q = 0; q < 8; q++)
-            if (q < world) v += t[q];
-        } else v = (src < nn) ? p.H[src] : p.b[src - nn];
-        if (src < nn && r == c) v += p.ep + p.lm * v;
-        if (envelope && v != 0.0 && r < nt * kT) {
-          const int tr = r >> 5, tc = c >> 5;
-          if (tc < tr && tc < *reinterpret_cast<volatile int*>(p.first + tr)) atomicMin(p.first + tr, tc);
+            for (int q = 0; q < 8; q++) {
+              t[u][q] = 0.0;
+              if (q < world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t[u][q]) : "l"(p.peers.sys[q] + srcs[u]) : "memory");
+            }
+          } else t[u][0] = (srcs[u] < nn) ? p.H[srcs[u]] : p.b[srcs[u] - nn];
         }
       }
-      stcg(L + idx, v);
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const size_t idx = base + u * stride;
+        if (idx >= total) continue;
+        double v = vals[u];
+        if (srcs[u] != (size_t)-1) {
+          // all peer loads were issued before the first add, then summed in fixed rank order: every rank computes the identical sum
+          if (world > 1) {
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+              if (q < world) v += t[u][q];
+          } else v = t[u][0];
+          const int r = (int)(idx / ld), c = (int)(idx - (size_t)r * ld);
+          if (srcs[u] < nn && r == c) v += p.ep + p.lm * v;
+          if (envelope && v != 0.0 && r < nt * kT) {
+            const int tr = r >> 5, tc = c >> 5;
+            if (tc < tr && tc < *reinterpret_cast<volatile int*>(p.first + tr)) atomicMin(p.first + tr, tc);
+          }
+        }
+        stcg(L + idx, v);
+      }
     }
   }
   CHOL_STAMP(0);

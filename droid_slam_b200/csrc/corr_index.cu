@@ -52,7 +52,13 @@ template <> struct CorrMath<__nv_bfloat16> {
 // ------------------------------------------------------------------------------------------------------
 // generic kernels: any radius, any extents, exact skip semantics.  One thread per pixel.
 // ------------------------------------------------------------------------------------------------------
-template <typename T>
+// element (y1, x1) of a plane: row-major, or the 4x8-tile layout [h2/4][w2/8][4][8] of corr_volume_pyramid's tiled mode
+template <bool TILED>
+__device__ __forceinline__ size_t plane_index(int y1, int x1, int w2) {
+  return TILED ? ((size_t)(y1 >> 2) * (w2 >> 3) + (x1 >> 3)) * 32 + (y1 & 3) * 8 + (x1 & 7) : (size_t)y1 * w2 + x1;
+}
+
+template <typename T, bool TILED = false>
 __device__ __forceinline__ void corr_pixel_generic(const T* __restrict__ plane, T* __restrict__ out_px, size_t out_stride,
                                                    float x0, float y0, int h2, int w2, int r) {
   typedef CorrMath<T> M;
@@ -70,17 +76,17 @@ __device__ __forceinline__ void corr_pixel_generic(const T* __restrict__ plane, 
       T acc = M::zero();
       const bool xa = (unsigned)x1 < (unsigned)w2, xb = (unsigned)(x1 + 1) < (unsigned)w2;
       const bool ya = (unsigned)y1 < (unsigned)h2, yb = (unsigned)(y1 + 1) < (unsigned)h2;
-      if (xa && ya) acc = M::mac(plane[(size_t)y1 * w2 + x1], w00, acc);
-      if (xa && yb) acc = M::mac(plane[(size_t)(y1 + 1) * w2 + x1], w01, acc);
-      if (xb && ya) acc = M::mac(plane[(size_t)y1 * w2 + x1 + 1], w10, acc);
-      if (xb && yb) acc = M::mac(plane[(size_t)(y1 + 1) * w2 + x1 + 1], w11, acc);
+      if (xa && ya) acc = M::mac(plane[plane_index<TILED>(y1, x1, w2)], w00, acc);
+      if (xa && yb) acc = M::mac(plane[plane_index<TILED>(y1 + 1, x1, w2)], w01, acc);
+      if (xb && ya) acc = M::mac(plane[plane_index<TILED>(y1, x1 + 1, w2)], w10, acc);
+      if (xb && yb) acc = M::mac(plane[plane_index<TILED>(y1 + 1, x1 + 1, w2)], w11, acc);
       out_px[(size_t)(i * rd + j) * out_stride] = acc;
     }
   }
 }
 
 template <>
-__device__ __forceinline__ void corr_pixel_generic<__nv_bfloat16>(const __nv_bfloat16* __restrict__ plane,
+__device__ __forceinline__ void corr_pixel_generic<__nv_bfloat16, false>(const __nv_bfloat16* __restrict__ plane,
                                                                   __nv_bfloat16* __restrict__ out_px, size_t out_stride,
                                                                   float x0, float y0, int h2, int w2, int r) {
   const float fxf = floorf(x0), fyf = floorf(y0);
@@ -199,13 +205,8 @@ __device__ __forceinline__ void align_row_f16(const uint4& A, const uint4& B, in
 template <bool TILED>
 __device__ __forceinline__ void corr_pixel_f16_r3(const __half* __restrict__ plane, __half* __restrict__ out_px, size_t out_stride,
                                                   float x0, float y0, int h2, int w2) {
-  if (!(isfinite(x0) && isfinite(y0))) {   // exact skip semantics for NaN/inf coordinates (nothing is in bounds -> zeros)
-    if (TILED) {
-#pragma unroll 1
-      for (int k = 0; k < 49; k++) out_px[(size_t)k * out_stride] = __float2half_rn(0.f);
-    } else {
-      corr_pixel_generic<__half>(plane, out_px, out_stride, x0, y0, h2, w2, 3);
-    }
+  if (!(isfinite(x0) && isfinite(y0))) {   // exact reference semantics for NaN/inf coordinates (slow path)
+    corr_pixel_generic<__half, TILED>(plane, out_px, out_stride, x0, y0, h2, w2, 3);
     return;
   }
   const float fxf = floorf(x0), fyf = floorf(y0);

@@ -242,3 +242,60 @@ extern "C" int dba_iproj(const float* poses, const float* disps, const float* in
   DBA_CHECK_LAUNCH("iproj");
   return DBA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// convex upsampling of the inverse depth maps (reference droid_slam/droid_net.py:21-42 `cvx_upsample` / `upsample_disp`, called by
+// DepthVideo.upsample, depth_video.py:155-159): out[b][8y+i][8x+j] = sum_k softmax_k(mask[b][k*64 + i*8 + j][y][x]) * d[b][y+ky-1][x+kx-1],
+// k = 3*ky + kx, zero padding (F.unfold).  One thread = one source pixel and one sub-row i: 72 coalesced mask loads (lanes run over x),
+// softmax over the 9 taps in fp32 (autocast runs softmax in fp32 too), 8 consecutive outputs = one 32-byte sector.
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace dba {
+template <typename TM>
+__global__ void __launch_bounds__(256) cvx_upsample_kernel(const float* __restrict__ disps, const TM* __restrict__ mask, float* __restrict__ out,
+                                                           int n, int ht, int wd) {
+  const int hw = ht * wd;
+  const long long total = (long long)n * 8 * hw;
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= total) return;
+  const int pin = (int)(id % hw);
+  const int i = (int)((id / hw) % 8);
+  const int b = (int)(id / (8LL * hw));
+  const int y = pin / wd, x = pin - y * wd;
+  float d[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+    d[k] = (yy >= 0 && yy < ht && xx >= 0 && xx < wd) ? __ldg(disps + (size_t)b * hw + (size_t)yy * wd + xx) : 0.f;
+  }
+  const TM* m = mask + ((size_t)b * 576 + i * 8) * hw + pin;
+  float res[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float v[9], mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { v[k] = (float)m[((size_t)k * 64 + j) * hw]; mx = fmaxf(mx, v[k]); }
+    float den = 0.f, num = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) { const float e = __expf(v[k] - mx); den += e; num += e * d[k]; }
+    res[j] = num / den;
+  }
+  float4* o = reinterpret_cast<float4*>(out + ((size_t)b * 8 * ht + 8 * y + i) * (size_t)(8 * wd) + 8 * x);
+  o[0] = make_float4(res[0], res[1], res[2], res[3]);
+  o[1] = make_float4(res[4], res[5], res[6], res[7]);
+}
+}  // namespace dba
+
+extern "C" int dba_cvx_upsample(const float* disps, const void* mask, float* out, int n, int ht, int wd, int mask_dtype, dba_stream_t stream) {
+  DBA_CHECK_ARG(n >= 0 && ht >= 0 && wd >= 0, "negative extent");
+  if (n == 0 || ht * wd == 0) return DBA_OK;
+  DBA_CHECK_ARG(disps && mask && out, "null pointer");
+  DBA_CHECK_ARG(mask_dtype == DBA_F16 || mask_dtype == DBA_F32, "mask must be f16 or f32");
+  DBA_CHECK_ARG((((uintptr_t)out) & 15) == 0, "out must be 16-byte aligned");
+  const long long total = (long long)n * 8 * ht * wd;
+  DBA_CHECK_ARG((total + 255) / 256 < 0x7fffffffLL, "too many pixels for one launch");
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (mask_dtype == DBA_F16) dba::cvx_upsample_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(disps, (const __half*)mask, out, n, ht, wd);
+  else dba::cvx_upsample_kernel<float><<<blocks, 256, 0, (cudaStream_t)stream>>>(disps, (const float*)mask, out, n, ht, wd);
+  DBA_CHECK_LAUNCH("cvx_upsample");
+  return DBA_OK;
+}

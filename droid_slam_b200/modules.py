@@ -13,7 +13,7 @@ import torch
 
 from . import install
 
-__all__ = ["install_corr_volume_hook", "reproject"]
+__all__ = ["install_corr_volume_hook", "reproject", "upsample"]
 
 
 def install_corr_volume_hook(corr_module, strict=True, fused_lookup=False):
@@ -57,3 +57,12 @@ def reproject(poses, disps, intrinsics, ii, jj):
     jj = torch.as_tensor(jj).to(device=poses.device, dtype=torch.long).reshape(-1)
     coords, valid = be.reproject(poses.contiguous(), disps.contiguous(), intrinsics.contiguous(), ii, jj)
     return coords[None], valid[None]
+
+
+def upsample(disps, disps_up, ix, mask):
+    """DepthVideo.upsample (reference droid_slam/depth_video.py:155-159) in one kernel: disps_up[ix] = cvx_upsample(disps[ix], mask).
+    disps [N,ht,wd] f32, disps_up [N,8ht,8wd] f32 (written in place), ix index tensor, mask [1,len(ix),576,ht,wd] (the update operator's upmask)."""
+    be = install()
+    m = mask.reshape(-1, 576, disps.shape[1], disps.shape[2]).contiguous()
+    disps_up[ix] = be.cvx_upsample(disps[ix].contiguous(), m)
+    return disps_up

@@ -112,6 +112,11 @@ int dba_depth_filter(const float* poses, const float* disps, const float* intrin
 int dba_iproj(const float* poses, const float* disps, const float* intrinsics, float* points /*[n,ht,wd,3]*/,
               int n, int ht, int wd, dba_stream_t stream);
 
+/* convex upsampling of inverse depth maps: replaces cvx_upsample / upsample_disp (reference droid_slam/droid_net.py:21-42) as called by
+ * DepthVideo.upsample (depth_video.py:155-159).  disps [n,ht,wd] f32, mask [n,576,ht,wd] (f16 or f32; 9 taps x 8 x 8 sub-pixels, the
+ * update operator's `upmask`), out [n,8*ht,8*wd] f32 = softmax-over-taps weighted sum of the 3x3 neighbourhood (zero padded). */
+int dba_cvx_upsample(const float* disps, const void* mask, float* out, int n, int ht, int wd, int mask_dtype, dba_stream_t stream);
+
 /* ---- dense bundle adjustment --------------------------------------------------------------------
  * replaces ba_cuda (reference src/droid_kernels.cu:1323-1443, bound at src/droid.cpp:93-122).
  * In place on poses [n_frames,7] and disps [n_frames,ht,wd]; disps_sens like disps; targets, weights

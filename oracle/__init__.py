@@ -18,3 +18,4 @@ from .geom import *     # noqa: F401,F403
 from .ba import *       # noqa: F401,F403
 from .corr import *     # noqa: F401,F403
 from .update import *   # noqa: F401,F403
+from .upsample import *  # noqa: F401,F403

@@ -59,6 +59,11 @@ def main(out_path):
             o2 = mod(net, inp, corr, None, None)                       # no flow, no aggregation
             for k, t in zip(("net", "delta", "weight"), o2):
                 G["%s_noflow_%s" % (name, k)] = t.clone()
+    # cvx_upsample (droid_net.py:21-35), the reference function itself, on seeded inputs
+    g = torch.Generator().manual_seed(321)
+    d = torch.rand(3, 6, 10, 1, generator=g) + 0.2
+    m = 2.0 * torch.randn(3, 576, 6, 10, generator=g)
+    G["cvx_upsample"] = droid_net.cvx_upsample(d, m).clone()
     torch.save(G, out_path)
     print("saved", out_path, os.path.getsize(out_path), "bytes;", len(G["state_dict_keys"]), "parameters")
 

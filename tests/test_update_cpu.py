@@ -85,3 +85,14 @@ def test_packed_dataflow_matches_oracle(weights, name, kw):
     ref3 = oracle.update_module_forward(weights, net, inp, corr)
     for a, b in zip(got3, [ref3[0][0].permute(0, 2, 3, 1), ref3[1][0], ref3[2][0]]):
         assert float((a - b).abs().max()) < 2e-3
+
+
+def test_cvx_upsample_oracle_matches_reference_function(gold):
+    """oracle.cvx_upsample vs the output of the reference's own cvx_upsample (droid_net.py:21-35, stored by make_update_golden.py)"""
+    g = torch.Generator().manual_seed(321)
+    d = torch.rand(3, 6, 10, 1, generator=g) + 0.2
+    m = 2.0 * torch.randn(3, 576, 6, 10, generator=g)
+    out = oracle.cvx_upsample(d, m)
+    assert out.shape == gold["cvx_upsample"].shape == (3, 48, 80, 1)
+    assert torch.allclose(out, gold["cvx_upsample"], rtol=1e-6, atol=1e-7)
+    assert torch.equal(oracle.upsample_disp(d[None, ..., 0], m[None]), out[None, ..., 0])

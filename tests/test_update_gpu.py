@@ -131,3 +131,22 @@ def test_update_module_rejects_cpu_tensors():
     net, inp, corr, flow, ii = synth.make_update_inputs(E=2, ht=8, wd=8, seed=0, n_src=1)
     with pytest.raises(RuntimeError):
         mod(net, inp, corr, flow, ii)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_cvx_upsample_kernel_matches_oracle(backends, dtype):
+    """DepthVideo.upsample's cvx_upsample (reference droid_net.py:21-42) in one kernel; f16 masks as the update operator emits them"""
+    g = torch.Generator().manual_seed(5)
+    n, ht, wd = 5, 48, 64
+    d = torch.rand(n, ht, wd, generator=g) + 0.1
+    m = (2.0 * torch.randn(n, 576, ht, wd, generator=g)).to(dtype)
+    got = backends.cvx_upsample(d.to(DEV), m.to(DEV))
+    ref = oracle.cvx_upsample(d[..., None], m.float())[..., 0]
+    assert got.shape == (n, 8 * ht, 8 * wd)
+    assert float((got.cpu() - ref).abs().max()) < 2e-6
+    from droid_slam_b200.modules import upsample
+    up = torch.zeros(8, 8 * ht, 8 * wd, device=DEV)
+    ix = torch.tensor([1, 3, 4, 6, 7], device=DEV)
+    disps = torch.zeros(8, ht, wd, device=DEV); disps[ix] = d.to(DEV)
+    upsample(disps, up, ix, m.to(DEV)[None])
+    assert torch.equal(up[ix], got) and float(up[0].abs().max()) == 0.0

@@ -71,6 +71,7 @@ def assert_bit_identical(a, b, what=""):
     a = a.cpu(); b = b.cpu()
     assert a.shape == b.shape and a.dtype == b.dtype, (what, a.shape, b.shape, a.dtype, b.dtype)
     if not torch.equal(a, b):
-        neq = (a != b) & ~(torch.isnan(a) & torch.isnan(b))
-        d = (a.double() - b.double()).abs()
-        raise AssertionError("%s: %d of %d elements differ, max |diff| %.3e" % (what, int(neq.sum()), a.numel(), float(d[neq].max()) if bool(neq.any()) else 0.0))
+        neq = (a != b) & ~(torch.isnan(a) & torch.isnan(b))          # NaN in the same place on both sides (NaN coordinates) counts as identical
+        if bool(neq.any()):
+            d = (a.double() - b.double()).abs()
+            raise AssertionError("%s: %d of %d elements differ, max |diff| %.3e" % (what, int(neq.sum()), a.numel(), float(d[neq].max())))
