@@ -297,13 +297,13 @@ std::vector<torch::Tensor> reproject(torch::Tensor poses, torch::Tensor disps, t
 // extension: the update operator (reference droid_slam/droid_net.py:111-143, modules/gru.py:19-32, droid_net.py:59-75) on the tensor
 // cores.  net [E,128,ht,wd] f16/f32 (or channels-last f16 [E,ht,wd,128] when net_channels_last), inp [E,128,ht,wd], corr [E,196,ht,wd],
 // flow [E,4,ht,wd] f32 or None, seg [E] int64 (torch.unique inverse of the source frames) or None, n_src distinct sources,
-// packed = the 26 tensors of droid_slam_b200.update.pack_update_weights in dba_update_weights order.
+// packed = the 27 tensors of droid_slam_b200.update.pack_update_weights in dba_update_weights order.
 // Returns [net' (channels-last f16 [E,ht,wd,128]), delta [E,ht,wd,2] f32, weight [E,ht,wd,2] f32 (, eta [n_src,ht,wd] f32, upmask [n_src,576,ht,wd] f16)].
 std::vector<torch::Tensor> update_forward(torch::Tensor net, torch::Tensor inp, torch::Tensor corr, c10::optional<torch::Tensor> flow,
                                           c10::optional<torch::Tensor> seg, int64_t n_src, std::vector<torch::Tensor> packed, bool net_channels_last) {
   CHECK_INPUT(net); CHECK_INPUT(inp); CHECK_INPUT(corr);
   TORCH_CHECK(net.dim() == 4 && inp.dim() == 4 && corr.dim() == 4, "net/inp/corr must be 4-D");
-  TORCH_CHECK(packed.size() == 26, "packed weights: 26 tensors expected");
+  TORCH_CHECK(packed.size() == 27, "packed weights: 27 tensors expected");
   c10::cuda::CUDAGuard guard(net.device());
   int E, ht, wd;
   if (net_channels_last) {
@@ -325,7 +325,7 @@ std::vector<torch::Tensor> update_forward(torch::Tensor net, torch::Tensor inp, 
   if (agg) { seg_c = seg->contiguous(); CHECK_CUDA(seg_c); CHECK_I64(seg_c); TORCH_CHECK(seg_c.numel() == E, "seg must have one entry per edge"); }
   dba_update_weights W;
   const void** wp = reinterpret_cast<const void**>(&W);
-  for (int k = 0; k < 26; k++) {
+  for (int k = 0; k < 27; k++) {
     CHECK_INPUT(packed[k]);
     TORCH_CHECK(packed[k].scalar_type() == (k < 12 ? torch::kFloat16 : torch::kFloat32), "packed weight ", k, " has the wrong dtype");
     wp[k] = packed[k].data_ptr();

@@ -106,16 +106,17 @@ struct CholParams {
 // one warp: C (32x32 at Ct) -= A (at At) * B^T (at Bt); lane (rg = lane>>3, cg = lane&7) owns rows 8rg..8rg+7, cols 4cg..4cg+3
 __device__ __forceinline__ void warp_tile_update(const double* At, const double* Bt, double* Ct, int ld, int lane,
                                                  double (*sA)[kTP], double (*sB)[kTP]) {
-#pragma unroll 16
-  for (int r = 0; r < kT; r++) { sA[r][lane] = ldcg(At + (size_t)r * ld + lane); sB[r][lane] = ldcg(Bt + (size_t)r * ld + lane); }
   const int rg = lane >> 3, cgp = lane & 7;
   double acc[8][4];
+  // the C tile's loads go out first and return under the operand staging (one L2 round trip instead of two)
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const double2 c01 = __ldcg(reinterpret_cast<const double2*>(Ct + (size_t)(8 * rg + i) * ld + 4 * cgp));
     const double2 c23 = __ldcg(reinterpret_cast<const double2*>(Ct + (size_t)(8 * rg + i) * ld + 4 * cgp + 2));
     acc[i][0] = c01.x; acc[i][1] = c01.y; acc[i][2] = c23.x; acc[i][3] = c23.y;
   }
+#pragma unroll 16
+  for (int r = 0; r < kT; r++) { sA[r][lane] = ldcg(At + (size_t)r * ld + lane); sB[r][lane] = ldcg(Bt + (size_t)r * ld + lane); }
   __syncwarp();
 #pragma unroll 4
   for (int q = 0; q < kT; q++) {
@@ -322,13 +323,18 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
         double a[kT];
         trsm_tile(k + 1, a);
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");          // barrier 1 (split phase): tile (k+1,k) is published
-        // T -= X X^T: lane = row r, X[r][.] in registers, X[c][.] broadcast from the warp's slab
+        // T -= X X^T: lane = row r, X[r][.] in registers, X[c][.] broadcast from the warp's slab; four columns at a time = four
+        // independent fp64 FMA chains (a dependent DFMA costs ~9 cycles, the warp issues one every 2)
 #pragma unroll
-        for (int c = 0; c < kT; c++) {
-          double acc0 = 0.0, acc1 = 0.0;
+        for (int c = 0; c < kT; c += 4) {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-          for (int q = 0; q < kT; q += 2) { acc0 = fma(a[q], s_A[warp][c][q], acc0); acc1 = fma(a[q + 1], s_A[warp][c][q + 1], acc1); }
-          tt[c] -= acc0 + acc1;
+          for (int q = 0; q < kT; q++) {
+            const double aq = a[q];
+            s0 = fma(aq, s_A[warp][c][q], s0); s1 = fma(aq, s_A[warp][c + 1][q], s1);
+            s2 = fma(aq, s_A[warp][c + 2][q], s2); s3 = fma(aq, s_A[warp][c + 3][q], s3);
+          }
+          tt[c] -= s0; tt[c + 1] -= s1; tt[c + 2] -= s2; tt[c + 3] -= s3;
         }
       } else {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -344,8 +350,24 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       }
       asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");               // barrier 1 complete (long since)
     } else {
-      // ---- TRSM of the other active rows (tile row nt is the right-hand side), spread over the 127 worker warps
-      for (int ta = t_first + gw - 1; ta < nact; ta += nwarps - 1) {
+      const int nwork = nwarps - 2;                     // worker warps 1 .. nwarps-2; the last warp only inverts L_kk (below)
+      const bool worker = gw < nwarps - 1;
+      if (!worker) {
+        // inverse of L_kk (for the backward substitution): lane j owns column j.  A 32-step dependent chain, so it gets a warp of its
+        // own and runs beside the TRSMs instead of after a tile update
+        double xcol[kT];
+#pragma unroll
+        for (int i = 0; i < kT; i++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int m = 0; m < i; m++) sacc += (m >= lane) ? s_Lkk[i][m] * xcol[m] : 0.0;
+          xcol[i] = (i == lane) ? s_rdiag[i] : ((i > lane) ? -sacc * s_rdiag[i] : 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
+      }
+      // ---- TRSM of the other active rows (tile row nt is the right-hand side), spread over the worker warps
+      for (int ta = t_first + gw - 1; worker && ta < nact; ta += nwork) {
         const int i = envelope ? s_act[ta] : k + 1 + ta;
         double a[kT];
         trsm_tile(i, a);
@@ -358,7 +380,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       // tile (task 0 when row k+1 is active) belongs to the chain warp
       const int ntri = m1 * (m1 + 1) / 2;
       const int ntasks = ntri + m1;
-      for (int t = t_first + gw - 1; t < ntasks; t += nwarps - 1) {
+      for (int t = t_first + gw - 1; worker && t < ntasks; t += nwork) {
         int i, j;
         if (t < ntri) {
           int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
@@ -372,19 +394,6 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       }
     }
     CHOL_STAMP_W(8 + 8 * k + 3);
-    // inverse of L_kk (for the backward substitution) by the last warp of the cluster: lane j owns column j
-    if (gw == nwarps - 1) {
-      double xcol[kT];
-#pragma unroll
-      for (int i = 0; i < kT; i++) {
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < i; m++) s += (m >= lane) ? s_Lkk[i][m] * xcol[m] : 0.0;
-        xcol[i] = (i == lane) ? s_rdiag[i] : ((i > lane) ? -s * s_rdiag[i] : 0.0);
-      }
-#pragma unroll
-      for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
-    }
     cluster.sync();
     CHOL_STAMP(8 + 8 * k + 4);
   }

@@ -27,7 +27,7 @@
 
 namespace dba {
 
-enum { EPI_STORE = 0, EPI_GATE = 1, EPI_ZR = 2, EPI_Q = 3, EPI_HEAD = 4, EPI_NCHW = 5 };
+enum { EPI_STORE = 0, EPI_GATE = 1, EPI_ZR = 2, EPI_Q = 3, EPI_F32 = 4, EPI_NCHW = 5 };
 
 constexpr int kUpThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr bool kPairDefault = false;   // cta_group::2 kernel by default
@@ -50,7 +50,7 @@ struct ConvParams {
   const float* glo;                 // [E][384] global-context terms: z | r | q
   __half* z; __half* rh;            // EPI_ZR outputs [pix][128]; EPI_Q reads z
   float* partial; int slots;        // EPI_GATE: [E][slots][128] column sums of sigmoid(.) * h over 32-pixel groups
-  float* f32a; float* f32b; int head_mode;   // EPI_HEAD: 0 = (delta | sigmoid weight), 1 = 0.01 * softplus (eta)
+  float* f32a; int f32_cols, f32_stride;      // EPI_F32: f32 out[pix * f32_stride + n] for n < f32_cols (per-tap partial sums of the narrow heads)
   __half* nchw; int nchw_C;         // EPI_NCHW: out[(img * nchw_C + n) * HT*WD + pixel]
 };
 
@@ -198,17 +198,12 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, uint32_t
           }
           store32h(p.out + pix * p.out_stride + c0, v);
         }
-      } else if (EPI == EPI_HEAD) {
-        if (valid && c0 == 0) {
-          if (p.head_mode == 0) {
-            p.f32a[pix * 2 + 0] = v[0];
-            p.f32a[pix * 2 + 1] = v[1];
-            p.f32b[pix * 2 + 0] = 1.f / (1.f + __expf(-v[2]));
-            p.f32b[pix * 2 + 1] = 1.f / (1.f + __expf(-v[3]));
-          } else {
-            const float xx = v[0];
-            p.f32a[pix] = 0.01f * (xx > 20.f ? xx : log1pf(__expf(xx)));     // torch Softplus(beta = 1, threshold = 20)
-          }
+      } else if (EPI == EPI_F32) {
+        if (valid) {
+          float* o = p.f32a + pix * p.f32_stride + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < p.f32_cols) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);     // f32_cols, f32_stride: multiples of 4
         }
       } else if (EPI == EPI_NCHW) {
         if (valid) {
@@ -644,6 +639,37 @@ __global__ void __launch_bounds__(256) flow_im2col_kernel(const float* __restric
   }
 }
 
+// The 3x3 convolutions with 1-2 output channels (delta.2, weight.2, agg.eta.0) are computed as ONE 1x1 convolution that produces, per
+// pixel, the 9 per-tap partial sums of every output (Y[p][t*no + o] = sum_c act[p][c] w[t][o][c]; on the tensor cores, the input is read
+// once instead of three times), followed by this gather: out[p][o] = bias[o] + sum_t Y[p + shift_t][t*no + o] (zero outside the image).
+// mode 0: no = 4 -> delta (o = 0,1) and sigmoid weight (o = 2,3), [img,ht,wd,2] each;  mode 1: no = 1 -> eta = 0.01 * softplus
+__global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ Y, int ystride, int no, const float* __restrict__ bias, int mode,
+                                                          float* __restrict__ out_a, float* __restrict__ out_b, int n_img, int HT, int WD) {
+  const long long total = (long long)n_img * HT * WD;
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= total) return;
+  const int HW = HT * WD;
+  const int pin = (int)(id % HW);
+  const long long img = id / HW;
+  const int y = pin / WD, x = pin - y * WD;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; t++) {
+    const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+    if (yy < 0 || yy >= HT || xx < 0 || xx >= WD) continue;
+    const float* q = Y + ((size_t)img * HW + (size_t)yy * WD + xx) * ystride + t * no;
+    if (no == 4) { const float4 v = __ldg(reinterpret_cast<const float4*>(q)); acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+    else acc[0] += __ldg(q);
+  }
+  if (mode == 0) {
+    *reinterpret_cast<float2*>(out_a + (size_t)id * 2) = make_float2(acc[0] + bias[0], acc[1] + bias[1]);
+    *reinterpret_cast<float2*>(out_b + (size_t)id * 2) = make_float2(1.f / (1.f + __expf(-(acc[2] + bias[2]))), 1.f / (1.f + __expf(-(acc[3] + bias[3]))));
+  } else {
+    const float xx = acc[0] + bias[0];
+    out_a[id] = 0.01f * (xx > 20.f ? xx : log1pf(__expf(xx)));     // torch Softplus(beta = 1, threshold = 20)
+  }
+}
+
 // global context (gru.py:25-30): g = mean over pixels of sigmoid(w(h)) * h (from the EPI_GATE partial sums), then the three 1x1
 // convolutions on g as one [384 x 128] mat-vec per edge -> glo[e][384] = z | r | q terms
 __global__ void __launch_bounds__(384) glo_kernel(const float* __restrict__ partial, int slots, float inv_hw, const float* __restrict__ wg /*[384][128]*/,
@@ -948,9 +974,13 @@ extern "C" int dba_update_forward(const dba_update_args* a) {
   const int stemN = n_src > 0 ? 384 : 256;
   { ConvParams p = base; p.KS = 3; p.N = stemN; p.w_rows = 384; p.bias = W->b_stem; p.relu = 1; p.out = S; p.out_stride = 384;
     rc = launch_conv<EPI_STORE>(p, ConvSrc{a->net_out, 128, 128}, none, W->w_stem, st); if (rc) return rc; }
-  // delta.2 and weight.2 (3x3 128->2 each) as one block-diagonal 256->4 convolution; sigmoid on the weight
-  { ConvParams p = base; p.KS = 3; p.N = 32; p.bias = W->b_heads; p.f32a = a->delta; p.f32b = a->weight; p.head_mode = 0;
-    rc = launch_conv<EPI_HEAD>(p, ConvSrc{S, 256, 384}, none, W->w_heads, st); if (rc) return rc; }
+  // delta.2 and weight.2 (3x3 128->2 each): per-tap partial sums by one 1x1 convolution 256 -> 36 (block-diagonal weights), then the
+  // 9-tap gather with bias / sigmoid
+  float* Yh = (float*)(ws + L.cc);                        // [E,HW,36] f32 on the (dead) corr staging buffer
+  { ConvParams p = base; p.KS = 1; p.N = 64; p.bias = W->b_zero; p.f32a = Yh; p.f32_cols = 36; p.f32_stride = 36;
+    rc = launch_conv<EPI_F32>(p, ConvSrc{S, 256, 384}, none, W->w_heads, st); if (rc) return rc; }
+  head_gather_kernel<<<(unsigned)(((size_t)E * HW + 255) / 256), 256, 0, st>>>(Yh, 36, 4, W->b_heads, 0, a->delta, a->weight, E, ht, wd);
+  DBA_CHECK_LAUNCH("head_gather_kernel");
   if (n_src > 0) {
     // ---- GraphAgg (droid_net.py:59-75): segment mean over edges with equal source frame, conv2, eta, upmask
     seg_csr_kernel<<<1, 256, (size_t)n_src * sizeof(int), st>>>(a->seg, E, n_src, seg_ptr, seg_edges);
@@ -959,8 +989,11 @@ extern "C" int dba_update_forward(const dba_update_args* a) {
     ConvParams fb = base; fb.E = n_src;
     { ConvParams p = fb; p.KS = 3; p.N = 128; p.bias = W->b_agg2; p.relu = 1; p.out = B2; p.out_stride = 128;
       rc = launch_conv<EPI_STORE>(p, ConvSrc{Am, 128, 128}, none, W->w_agg2, st); if (rc) return rc; }
-    { ConvParams p = fb; p.KS = 3; p.N = 32; p.bias = W->b_eta; p.f32a = a->eta; p.head_mode = 1;
-      rc = launch_conv<EPI_HEAD>(p, ConvSrc{B2, 128, 128}, none, W->w_eta, st); if (rc) return rc; }
+    float* Ye = (float*)(ws + L.f0);                      // [n_src,HW,12] f32 (9 used) on the (dead) flow im2col buffer
+    { ConvParams p = fb; p.KS = 1; p.N = 32; p.bias = W->b_zero; p.f32a = Ye; p.f32_cols = 12; p.f32_stride = 12;
+      rc = launch_conv<EPI_F32>(p, ConvSrc{B2, 128, 128}, none, W->w_eta, st); if (rc) return rc; }
+    head_gather_kernel<<<(unsigned)(((size_t)n_src * HW + 255) / 256), 256, 0, st>>>(Ye, 12, 1, W->b_eta, 1, a->eta, nullptr, n_src, ht, wd);
+    DBA_CHECK_LAUNCH("head_gather_kernel(eta)");
     { ConvParams p = fb; p.KS = 1; p.N = 192; p.n_ntiles = 3; p.bias = W->b_upmask; p.nchw = (__half*)a->upmask; p.nchw_C = 576;
       rc = launch_conv<EPI_NCHW>(p, ConvSrc{B2, 128, 128}, none, W->w_upmask, st); if (rc) return rc; }
   }

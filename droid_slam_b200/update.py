@@ -16,7 +16,7 @@ __all__ = ["ConvGRU", "GraphAgg", "UpdateModule", "pack_update_weights", "PACKED
 # order of dba_update_weights (include/droid_b200.h)
 PACKED_ORDER = ("w_corr0", "w_corr2", "w_flow0", "w_flow2", "w_gate", "w_zr", "w_q", "w_stem", "w_heads", "w_agg2", "w_eta", "w_upmask",
                 "b_corr0", "b_corr2", "b_flow0", "b_flow2", "b_gate", "b_zr", "b_q", "b_stem", "b_heads", "b_agg2", "b_eta", "b_upmask",
-                "w_glo", "b_glo")
+                "w_glo", "b_glo", "b_zero")
 
 
 def _conv(name):
@@ -43,7 +43,7 @@ def _padn(t, n):
 
 
 def pack_update_weights(sd, device=None):
-    """state_dict of the update operator (reference names) -> dict of the 26 packed tensors the kernels read (layouts: droid_b200.h).
+    """state_dict of the update operator (reference names) -> dict of the 27 packed tensors the kernels read (layouts: droid_b200.h).
     Pure tensor re-arrangement; f16 for the tensor-core operands, f32 for biases and the global-context mat-vec."""
     f = {k: v.detach().float() for k, v in sd.items()}
     W = {}
@@ -56,12 +56,15 @@ def pack_update_weights(sd, device=None):
     W["w_zr"] = _taps(torch.cat([f["gru.convz.weight"], f["gru.convr.weight"]], 0))
     W["w_q"] = _taps(f["gru.convq.weight"])
     W["w_stem"] = _taps(torch.cat([f["delta.0.weight"], f["weight.0.weight"], f["agg.conv1.weight"]], 0))
-    hd = torch.zeros(9, 32, 256)
-    hd[:, 0:2, 0:128] = _taps(f["delta.2.weight"][:2])
-    hd[:, 2:4, 128:256] = _taps(f["weight.2.weight"][:2])
+    # the 3x3 / 2-channel heads as per-tap rows of one 1x1 convolution: row 4t+o = tap t of output o (delta x,y | weight x,y)
+    hd = torch.zeros(1, 64, 256)
+    hd[0, :36, :].view(9, 4, 256)[:, 0:2, 0:128] = _taps(f["delta.2.weight"][:2])
+    hd[0, :36, :].view(9, 4, 256)[:, 2:4, 128:256] = _taps(f["weight.2.weight"][:2])
     W["w_heads"] = hd
     W["w_agg2"] = _taps(f["agg.conv2.weight"])
-    W["w_eta"] = _padn(_taps(f["agg.eta.0.weight"]), 32)
+    we = torch.zeros(1, 32, 128)
+    we[0, :9] = _taps(f["agg.eta.0.weight"])[:, 0, :]                     # row t = tap t
+    W["w_eta"] = we
     W["w_upmask"] = _taps(f["agg.upmask.0.weight"])
     W["b_corr0"] = f["corr_encoder.0.bias"]; W["b_corr2"] = f["corr_encoder.2.bias"]
     W["b_flow0"] = f["flow_encoder.0.bias"]; W["b_flow2"] = f["flow_encoder.2.bias"]
@@ -69,12 +72,13 @@ def pack_update_weights(sd, device=None):
     W["b_zr"] = torch.cat([f["gru.convz.bias"], f["gru.convr.bias"]])
     W["b_q"] = f["gru.convq.bias"]
     W["b_stem"] = torch.cat([f["delta.0.bias"], f["weight.0.bias"], f["agg.conv1.bias"]])
-    W["b_heads"] = _padn(torch.cat([f["delta.2.bias"][:2], f["weight.2.bias"][:2]]), 32)
+    W["b_heads"] = torch.cat([f["delta.2.bias"][:2], f["weight.2.bias"][:2]])
     W["b_agg2"] = f["agg.conv2.bias"]
-    W["b_eta"] = _padn(f["agg.eta.0.bias"], 32)
+    W["b_eta"] = f["agg.eta.0.bias"][:1]
     W["b_upmask"] = f["agg.upmask.0.bias"]
     W["w_glo"] = torch.cat([f["gru.convz_glo.weight"], f["gru.convr_glo.weight"], f["gru.convq_glo.weight"]], 0).reshape(384, 128)
     W["b_glo"] = torch.cat([f["gru.convz_glo.bias"], f["gru.convr_glo.bias"], f["gru.convq_glo.bias"]])
+    W["b_zero"] = torch.zeros(64)
     out = {}
     for i, k in enumerate(PACKED_ORDER):
         t = W[k].to(torch.float16 if i < 12 else torch.float32).contiguous()

@@ -189,12 +189,14 @@ int dba_ba_read_info(const dba_ba_args* a, int* n_depth_frames, int* device_stat
  *   w_gate  [1][128][128]  gru.w          w_glo f32 [384][128] = gru.convz_glo | convr_glo | convq_glo, b_glo [384]
  *   w_zr    [9][256][448]  gru.convz | gru.convr         w_q [9][128][448] gru.convq
  *   w_stem  [9][384][128]  delta.0 | weight.0 | agg.conv1
- *   w_heads [9][32][256]   rows 0-1 = delta.2 on K 0..127, rows 2-3 = weight.2 on K 128..255, rest 0;  b_heads [32]
- *   w_agg2  [9][128][128]  agg.conv2      w_eta [9][32][128] row 0 = agg.eta.0, b_eta [32]      w_upmask [1][576][128] agg.upmask.0 */
+ *   w_heads [1][64][256]   per-tap rows: row 4t+o (t = 3 dy + dx) = tap t of delta.2 (o = 0,1; K 0..127) / weight.2 (o = 2,3; K 128..255),
+ *                          rows 36..63 zero -- the 3x3 / 2-channel heads run as one 1x1 convolution + a 9-tap gather;  b_heads [4]
+ *   w_agg2  [9][128][128]  agg.conv2      w_eta [1][32][128] row t = tap t of agg.eta.0, b_eta [1]      w_upmask [1][576][128] agg.upmask.0
+ *   b_zero  f32 [64] zeros (bias of the per-tap partial-sum convolutions) */
 typedef struct {
   const void *w_corr0, *w_corr2, *w_flow0, *w_flow2, *w_gate, *w_zr, *w_q, *w_stem, *w_heads, *w_agg2, *w_eta, *w_upmask;
   const float *b_corr0, *b_corr2, *b_flow0, *b_flow2, *b_gate, *b_zr, *b_q, *b_stem, *b_heads, *b_agg2, *b_eta, *b_upmask;
-  const float *w_glo, *b_glo;
+  const float *w_glo, *b_glo, *b_zero;
 } dba_update_weights;
 
 typedef struct {

@@ -61,8 +61,8 @@ def test_packed_weights_layout(weights):
     pk = pack_update_weights(weights)
     assert tuple(pk.keys()) == PACKED_ORDER
     shapes = dict(w_corr0=(1, 128, 256), w_corr2=(9, 128, 128), w_flow0=(1, 128, 256), w_flow2=(9, 64, 128), w_gate=(1, 128, 128),
-                  w_zr=(9, 256, 448), w_q=(9, 128, 448), w_stem=(9, 384, 128), w_heads=(9, 32, 256), w_agg2=(9, 128, 128), w_eta=(9, 32, 128),
-                  w_upmask=(1, 576, 128), w_glo=(384, 128), b_glo=(384,), b_heads=(32,), b_eta=(32,), b_zr=(256,), b_stem=(384,))
+                  w_zr=(9, 256, 448), w_q=(9, 128, 448), w_stem=(9, 384, 128), w_heads=(1, 64, 256), w_agg2=(9, 128, 128), w_eta=(1, 32, 128),
+                  w_upmask=(1, 576, 128), w_glo=(384, 128), b_glo=(384,), b_heads=(4,), b_eta=(1,), b_zr=(256,), b_stem=(384,), b_zero=(64,))
     for k, sh in shapes.items():
         assert tuple(pk[k].shape) == sh, k
     for i, k in enumerate(PACKED_ORDER):

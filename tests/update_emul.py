@@ -21,6 +21,17 @@ def conv_taps(x, wpk, bias, ks):
     return out + bias[: out.shape[-1]]
 
 
+def gather9(y, no):
+    """y [E,H,W,9*no] per-tap partial sums -> [E,H,W,no]: out[p] = sum_t y[p + shift_t][t*no:(t+1)*no] (zero outside)"""
+    E, H, W, _ = y.shape
+    yp = F.pad(y, (0, 0, 1, 1, 1, 1))
+    out = 0
+    for t in range(9):
+        dy, dx = t // 3, t % 3
+        out = out + yp[:, dy:dy + H, dx:dx + W, t * no:(t + 1) * no]
+    return out
+
+
 def emulate(pk, net, inp, corr, flow, seg, n_src, round16=False):
     """net/inp [E,128,H,W], corr [E,196,H,W], flow [E,4,H,W] or None, seg [E] or None -> net' [E,H,W,128], delta, weight [E,H,W,2], eta [n_src,H,W], upmask [n_src,576,H,W]"""
     r = (lambda t: t.half().float()) if round16 else (lambda t: t)
@@ -48,7 +59,7 @@ def emulate(pk, net, inp, corr, flow, seg, n_src, round16=False):
     hn = r((1 - z) * h + z * q)
     n_stem = 384 if seg is not None else 256
     s = r(F.relu(conv_taps(hn, pk["w_stem"][:, :n_stem], pk["b_stem"][:n_stem], 3)))
-    hd = conv_taps(s[..., :256], pk["w_heads"], pk["b_heads"], 3)
+    hd = gather9(conv_taps(s[..., :256], pk["w_heads"], pk["b_zero"], 1)[..., :36], 4) + pk["b_heads"]
     delta, weight = hd[..., 0:2], torch.sigmoid(hd[..., 2:4])
     if seg is None:
         return hn, delta, weight
@@ -56,6 +67,6 @@ def emulate(pk, net, inp, corr, flow, seg, n_src, round16=False):
     am = torch.zeros(n_src, H, W, 128).index_add_(0, seg, a1) / torch.bincount(seg, minlength=n_src).float().view(-1, 1, 1, 1)
     am = r(am)
     b2 = r(F.relu(conv_taps(am, pk["w_agg2"], pk["b_agg2"], 3)))
-    eta = 0.01 * F.softplus(conv_taps(b2, pk["w_eta"], pk["b_eta"], 3)[..., 0])
+    eta = 0.01 * F.softplus(gather9(conv_taps(b2, pk["w_eta"], pk["b_zero"], 1)[..., :9], 1)[..., 0] + pk["b_eta"][0])
     up = conv_taps(b2, pk["w_upmask"], pk["b_upmask"], 1).permute(0, 3, 1, 2)
     return hn, delta, weight, eta, up
