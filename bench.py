@@ -51,6 +51,8 @@ CONFIGS = {
     "c3": dict(edges=2048, frames=400, ht=48, wd=64, dtype="f16", itrs=10, lm=1e-5, ep=1e-2, scaling="strong", corr=False, stereo=False),
     "c4": dict(edges=256, frames=64, ht=48, wd=64, dtype="f16", itrs=2, lm=1e-4, ep=0.1, scaling="weak", corr=True, stereo=True),
     "c5": dict(edges=8192, frames=1000, ht=72, wd=96, dtype="bf16", itrs=2, lm=1e-4, ep=0.1, scaling="strong", corr=True, stereo=False),
+    # one rank's share of c5 on ONE GPU (1024 edges = 130 GB of bf16 volumes, 125 keyframes): the single-GPU proxy of the stress config
+    "c5_rank": dict(edges=1024, frames=125, ht=72, wd=96, dtype="bf16", itrs=2, lm=1e-4, ep=0.1, scaling="strong", corr=True, stereo=False),
 }
 
 
@@ -154,12 +156,19 @@ def build_problem(args, rank, world, dev):
     """the rank's shard of the (512*world)-edge graph: BA tensors, correlation pyramid, lookup coordinates"""
     from droid_slam_b200 import sharded, synth
     cfg = dict(E=EDGES_PER_GPU * (world if SCALING == "weak" else 1), N=FRAMES, ht=HT, wd=WD, stereo=STEREO, itrs=BA_ITERS, lm=LM, ep=EP)
-    s = synth.make_scene(cfg, seed=0)
+    on_device = cfg["E"] * HT * WD > 16 * 1024 * 1024     # the stress config's scene (57 M pixels x edges) is generated on the GPU: minutes -> seconds
+    s = synth.make_scene(cfg, seed=0, device=dev if on_device else "cpu")
     bounds = sharded.partition_frames(s["ii"], FRAMES, world)
     lo, hi = bounds[rank]
     idx = sharded.shard_edges(s["ii"], lo, hi)
     dtype = {"f16": torch.float16, "f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
-    sub = dict(s); sub["ii"] = s["ii"][idx]; sub["jj"] = s["jj"][idx]; sub["coords_gt"] = s["coords_gt"][idx]
+    sub = dict(s); sub["ii"] = s["ii"][idx]; sub["jj"] = s["jj"][idx]; sub["coords_gt"] = s["coords_gt"][idx.to(s["coords_gt"].device)]
+    if on_device:                                           # keep only this rank's shard, on the host like the CPU-generated scenes
+        ix = idx.to(dev)
+        s = dict(s, targets=s["targets"][ix].cpu(), weights=s["weights"][ix].cpu(), coords_gt=None, **{k: s[k].cpu() for k in ("poses", "disps", "disps_sens", "intrinsics", "eta", "poses_gt", "disps_gt")})
+        idx_local = torch.arange(int(idx.numel()))
+    else:
+        idx_local = idx
     sub["cfg"] = dict(cfg, E=int(idx.numel()))
     if WITH_CORR:
         need = int(idx.numel()) * (HT * WD) ** 2 * 1.33 * (4 if dtype == torch.float32 else 2)
@@ -171,8 +180,8 @@ def build_problem(args, rank, world, dev):
         pyr, coords = [], torch.zeros(int(idx.numel()), 2, HT, WD, device=dev)
     kx = torch.unique(torch.cat([torch.arange(s["t0"], s["t1"]), s["ii"]]))
     eta_f = torch.zeros(FRAMES, HT, WD); eta_f[kx] = s["eta"]
-    host = dict(poses=s["poses"], disps=s["disps"], disps_sens=s["disps_sens"], intrinsics=s["intrinsics"], targets=s["targets"][idx].contiguous(),
-                weights=s["weights"][idx].contiguous(), eta=s["eta"], eta_by_frame=eta_f, ii=sub["ii"].contiguous(), jj=sub["jj"].contiguous(),
+    host = dict(poses=s["poses"], disps=s["disps"], disps_sens=s["disps_sens"], intrinsics=s["intrinsics"], targets=s["targets"][idx_local].contiguous(),
+                weights=s["weights"][idx_local].contiguous(), eta=s["eta"], eta_by_frame=eta_f, ii=sub["ii"].contiguous(), jj=sub["jj"].contiguous(),
                 coords=coords.cpu())
     return dict(scene=s, host=host, bounds=bounds, pyr=pyr, coords=coords, E=int(idx.numel()), dtype=dtype, t0=s["t0"], t1=s["t1"], M=s["M"])
 

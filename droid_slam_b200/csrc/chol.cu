@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       const bool worker = gw < nwarps - 1;
       if (!worker) {
         // inverse of L_kk (for the backward substitution): lane j owns column j.  A 32-step dependent chain, so it gets a warp of its
-        // own and runs beside the TRSMs instead of after a tile update
+        // own: it arrives at barrier 1 at once (it publishes nothing the trailing updates need) and works beside the TRSMs and updates
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         double xcol[kT];
 #pragma unroll
         for (int i = 0; i < kT; i++) {
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
         }
 #pragma unroll
         for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
       }
       // ---- TRSM of the other active rows (tile row nt is the right-hand side), spread over the worker warps
       for (int ta = t_first + gw - 1; worker && ta < nact; ta += nwork) {
@@ -373,8 +375,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
         trsm_tile(i, a);
       }
       CHOL_STAMP_W(8 + 8 * k + 1);
-      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");                // barrier 1: every TRSM'd tile of panel k is visible
+      if (worker) {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");              // barrier 1: every TRSM'd tile of panel k is visible
+      }
       CHOL_STAMP_W(8 + 8 * k + 2);
       // ---- trailing update with panel k: tiles (i,j) of active rows, j <= i < nt, plus the rhs row tiles (nt,j); the next diagonal
       // tile (task 0 when row k+1 is active) belongs to the chain warp

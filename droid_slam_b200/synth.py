@@ -116,12 +116,16 @@ def make_graph(E, N, stereo=False, seed=0, t0=1):
     return ii, jj
 
 
-def make_scene(cfg="metric", seed=0, rgbd=False, **over):
+def make_scene(cfg="metric", seed=0, rgbd=False, device="cpu", **over):
     """Full BA problem for a named config: dict with poses, disps, disps_sens, intrinsics, targets, weights, eta, ii, jj,
-    t0, t1, itrs, lm, ep, plus the ground truth (poses_gt, disps_gt)."""
+    t0, t1, itrs, lm, ep, plus the ground truth (poses_gt, disps_gt).
+    device: where the per-pixel tensors are generated (default CPU; a CUDA device draws from that device's seeded generator -- a
+    different but equally deterministic scene, used for the stress config whose 8192-edge scene takes minutes on the host)."""
     c = dict(CONFIGS[cfg]) if isinstance(cfg, str) else dict(cfg)
     c.update(over)
     E, N, ht, wd = c["E"], c["N"], c["ht"], c["wd"]
+    if str(device) != "cpu":
+        return _make_scene_on_device(c, seed, rgbd, torch.device(device))
     g = torch.Generator().manual_seed(1234 + seed)
     intr = torch.tensor([0.8 * 320 / 8 * (wd / 64), 0.8 * 320 / 8 * (wd / 64), wd / 2 - 0.5, ht / 2 - 0.5], dtype=torch.float64)
     k = torch.arange(N, dtype=torch.float64)[:, None]
@@ -160,6 +164,62 @@ def make_scene(cfg="metric", seed=0, rgbd=False, **over):
                 poses_gt=f32(poses_gt), disps_gt=f32(disps_gt), coords_gt=f32(coords))
 
 
+def _make_scene_on_device(c, seed, rgbd, dev):
+    """make_scene with the per-pixel work on a CUDA device (same construction, device-side random streams); returns CPU-free tensors
+    on `dev` except ii/jj (CPU, like make_scene)"""
+    E, N, ht, wd = c["E"], c["N"], c["ht"], c["wd"]
+    g = torch.Generator(device=dev).manual_seed(1234 + seed)
+    f64 = dict(dtype=torch.float64, device=dev)
+    intr = torch.tensor([0.8 * 320 / 8 * (wd / 64), 0.8 * 320 / 8 * (wd / 64), wd / 2 - 0.5, ht / 2 - 0.5], **f64)
+    k = torch.arange(N, **f64)[:, None]
+    xi = k * torch.tensor([0.05, 0.0, 0.02, 0.0, 0.01, 0.0], **f64) + 0.01 * torch.randn(N, 6, generator=g, **f64)
+    poses_gt = se3_exp(xi)
+    low = torch.randn(N, 1, max(2, ht // 8), max(2, wd // 8), generator=g, **f64)
+    disps_gt = (1.0 + 0.3 * F.interpolate(low, size=(ht, wd), mode="bilinear", align_corners=True)[:, 0]).clamp(0.1, 4.0)
+    if c.get("graph") is not None:
+        ii, jj = (torch.as_tensor(x, dtype=torch.long) for x in c["graph"])
+    else:
+        ii, jj = make_graph(E, N, stereo=c.get("stereo", False), seed=seed)
+    E = ii.shape[0]
+    t0 = c.get("t0", 1); t1 = c.get("t1", N)
+    iid, jjd = ii.to(dev), jj.to(dev)
+    # reprojection in edge chunks (the [E,ht,wd,3] fp64 intermediates of 8192 edges at 72x96 would not fit comfortably at once)
+    coords = torch.empty(E, ht, wd, 2, **f64); z_true = torch.empty(E, ht, wd, **f64)
+    fx, fy, cx, cy = [float(v) for v in intr]
+    v, u = torch.meshgrid(torch.arange(ht, **f64), torch.arange(wd, **f64), indexing="ij")
+    Xn = torch.stack([(u - cx) / fx, (v - cy) / fy, torch.ones_like(u)], -1)
+    for s0 in range(0, E, 512):
+        sl = slice(s0, min(E, s0 + 512))
+        G = se3_mul(poses_gt[jjd[sl]], se3_inv(poses_gt[iid[sl]]))
+        st = iid[sl] == jjd[sl]
+        if bool(st.any()):
+            G = G.clone(); G[st] = torch.tensor([-0.1, 0, 0, 0, 0, 0, 1], **f64)
+        Y = _qrot(G[:, None, None, 3:], Xn.expand(G.shape[0], ht, wd, 3)) + disps_gt[iid[sl]][..., None] * G[:, None, None, :3]
+        z = Y[..., 2].clamp(min=1e-3)
+        coords[sl] = torch.stack([fx * Y[..., 0] / z + cx, fy * Y[..., 1] / z + cy], -1); z_true[sl] = Y[..., 2]
+    targets = coords + 0.5 * torch.randn(E, ht, wd, 2, generator=g, **f64)
+    weights = torch.rand(E, ht, wd, 2, generator=g, **f64)
+    weights = torch.where(torch.rand(E, ht, wd, 2, generator=g, device=dev) < 0.1, torch.zeros_like(weights), weights)
+    visible = (z_true > 0.5) & (coords[..., 0] > -wd) & (coords[..., 0] < 2 * wd) & (coords[..., 1] > -ht) & (coords[..., 1] < 2 * ht)
+    weights = weights * visible[..., None].to(weights.dtype)
+    targets = torch.where(visible[..., None], targets, torch.zeros_like(targets))
+    kx = torch.unique(torch.cat([torch.arange(t0, t1), ii]))
+    M = kx.shape[0]
+    eta = 0.2 * 0.01 * F.softplus(torch.randn(M, ht, wd, generator=g, **f64)) + 1e-7
+    poses = se3_mul(se3_exp(0.02 * torch.randn(N, 6, generator=g, **f64)), poses_gt)
+    poses[:t0] = poses_gt[:t0]
+    disps = disps_gt * torch.exp(0.1 * torch.randn(N, ht, wd, generator=g, **f64))
+    if rgbd:
+        disps_sens = torch.where(torch.rand(N, ht, wd, generator=g, device=dev) < 0.5, disps_gt, torch.zeros_like(disps_gt))
+    else:
+        disps_sens = torch.zeros_like(disps_gt)
+    f32 = lambda x: x.float().contiguous()
+    return dict(cfg=c, poses=f32(poses), disps=f32(disps), disps_sens=f32(disps_sens), intrinsics=f32(intr),
+                targets=f32(targets.permute(0, 3, 1, 2)), weights=f32(weights.permute(0, 3, 1, 2)), eta=f32(eta),
+                ii=ii, jj=jj, t0=t0, t1=t1, itrs=c["itrs"], lm=c["lm"], ep=c["ep"], M=M,
+                poses_gt=f32(poses_gt), disps_gt=f32(disps_gt), coords_gt=f32(coords))
+
+
 def make_corr_inputs(scene, dtype=torch.float16, seed=0, channels=128, device="cpu", levels=4, edge_chunk=32):
     """feature maps ~ N(0,1), the 4-level correlation pyramid built with the reference formula (modules/corr.py:63-71,
     24-38) and lookup coordinates = true reprojection + U(-2,2)  (~3 % of windows cross the border).
@@ -170,7 +230,7 @@ def make_corr_inputs(scene, dtype=torch.float16, seed=0, channels=128, device="c
     ii, jj = scene["ii"], scene["jj"]
     E = ii.shape[0]
     fmaps = torch.randn(N, channels, ht, wd, generator=g).to(device=device, dtype=dtype)
-    coords = scene["coords_gt"] + (4 * torch.rand(E, ht, wd, 2, generator=g) - 2)
+    coords = scene["coords_gt"] + (4 * torch.rand(E, ht, wd, 2, generator=g) - 2).to(scene["coords_gt"].device)
     coords = coords.permute(0, 3, 1, 2).contiguous().to(device)
     pyr = [torch.empty(E, ht, wd, ht // 2 ** l, wd // 2 ** l, dtype=dtype, device=device) for l in range(levels)]
     for s in range(0, E, edge_chunk):
