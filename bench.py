@@ -76,7 +76,7 @@ def parse():
     ap.add_argument("--config", default="metric", choices=sorted(CONFIGS.keys()), help="BASELINE.json config (default: the one the metric is quoted on)")
     ap.add_argument("--dtype", default=None, choices=["f16", "f32", "bf16"], help="correlation volume dtype (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"], help="N>1: fused peer-to-peer reduction inside the solve kernel (default) or a NCCL all-reduce of the pose system")
+    ap.add_argument("--collective", default="auto", choices=["auto", "p2p", "nccl"], help="N>1: fused peer-to-peer reduction inside the solve kernel, or a NCCL all-reduce of the pose system; auto = p2p for pose systems up to 1024 unknowns (the metric window), nccl for the large global-BA systems (only 16 SMs pull peer data in the fused kernel)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a captured CUDA graph (N=1)")
     ap.add_argument("--dropin-lookup", action="store_true", help="time the step with the four drop-in corr_index_forward launches on reference-layout volumes (round-1 definition) instead of the fused one-launch lookup on tiled volumes")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernels (update operator, volume build, altcorr, geometry, solve) timed for `rooflines`")
@@ -221,6 +221,8 @@ def run_ours(args, rank, world, dev):
     spbox = [sp]
     engine = sharded.CApiEngine(dev)
     p2p = None
+    if args.collective == "auto":
+        args.collective = "p2p" if 6 * (pb["t1"] - pb["t0"]) <= 1024 else "nccl"
     if world > 1 and args.collective == "p2p":
         try:
             p2p = sharded.P2PSystem(6 * (pb["t1"] - pb["t0"]), dev)
