@@ -793,6 +793,9 @@ __global__ void __launch_bounds__(kSgThreads, 2) ba_schur_small_kernel(
 // it streams whether they are live or not), and the epilogue adds the two blocks.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kTcRowsMax = 21;
+constexpr int kPairTileRows = 10;               // pair mode: row tiles of 10 frame rows (60 lines + the w line <= 64 operand rows)
+constexpr int kPairRowsMax = 100;               // pair mode handles 22..100 rows (up to 45 tile pairs over gridDim.z); more rows: SIMT kernel
+constexpr int kPairGridZ = 45;
 constexpr int kTcThreads = 288;
 constexpr int kTcProducers = 256;
 constexpr int kTcRawStages = 4;
@@ -823,6 +826,12 @@ __device__ __forceinline__ unsigned long long tc_gtimer() { unsigned long long t
 #define TC_STAMP(cond, idx) do {} while (0)
 #endif
 
+// PAIR mode (frames with 22..100 rows: dense graphs, edge-sharded ranks): the rows are cut into tiles of 10; CTA (frame, pair z) stacks
+// tile a in operand rows 0..63 and tile b in rows 64..127 over the SAME 32 pixels (the packed layout with a zero pixel offset for the
+// second half), so the one M = N = 128 product holds S_ba in its lower-left block and S_aa / S_bb on the diagonal (emitted only by
+// the designated pair (t, t+1)); G + G^T symmetrisation unchanged.  Off-diagonal-block entries go to (max, min) of the global
+// indices and count twice where two different rows share a pose.
+template <bool PAIR>
 __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
     const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
     const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
@@ -844,19 +853,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
   extern __shared__ uint8_t tc_smem_raw[];
 
   if (deg == 0) return;                           // no out-edge (e.g. a frame another rank owns): E_k = 0, nothing to subtract
+  if (PAIR) {                                     // cheap exits before the row-list build: at most deg + 1 rows
+    if (deg + 1 <= kTcRowsMax) return;
+    const int tmax = (min(deg + 1, kPairRowsMax) + kPairTileRows - 1) / kPairTileRows;
+    if ((int)blockIdx.z >= tmax * (tmax - 1) / 2) return;
+  }
   build_row_list<kTcThreads>(jj, hdr, edgeidx, e_begin, deg, ix, m, HW, t0, P, Eij, Eiin, s_pose, s_ptr, &s_nrows, s_wcount);
   const int nrows = s_nrows;
-  if (nrows == 0 || nrows > kTcRowsMax) return;         // larger frames belong to ba_schur_gemm_kernel
+  if (!PAIR && (nrows == 0 || nrows > kTcRowsMax)) return;            // larger frames belong to the pair-mode launch / ba_schur_gemm_kernel
+  if (PAIR && (nrows <= kTcRowsMax || nrows > kPairRowsMax)) return;
+  int ta = 0, tb = 0;                                    // PAIR: the two row tiles of this CTA (ta < tb)
+  bool emit_a = true, emit_b = true;
+  if (PAIR) {
+    const int T = (nrows + kPairTileRows - 1) / kPairTileRows;         // >= 3
+    const int pr = blockIdx.z;
+    if (pr >= T * (T - 1) / 2) return;
+    tb = (int)((sqrtf(8.f * (float)pr + 1.f) + 1.f) * 0.5f);
+    while (tb * (tb - 1) / 2 > pr) tb--;
+    while ((tb + 1) * tb / 2 <= pr) tb++;
+    ta = pr - tb * (tb - 1) / 2;
+    emit_a = (tb == ta + 1);                             // S_tt of tile t < T-1 comes from pair (t, t+1), of tile T-1 from pair (T-2, T-1)
+    emit_b = (tb == T - 1 && ta == T - 2);
+  }
   const int px_begin = blockIdx.x * px_per_cta;
   const int px_end = min(HW, px_begin + px_per_cta);
   if (px_begin >= px_end) return;
-  const int R6 = 6 * nrows;                              // operand rows 0..R6-1: E rows, row R6: w
+  const int R6a = PAIR ? 6 * min(kPairTileRows, nrows - kPairTileRows * ta) : 6 * nrows;
+  const int R6b = PAIR ? 6 * min(kPairTileRows, nrows - kPairTileRows * tb) : 6 * nrows;
+  const int R6 = R6a;                                    // operand rows 0..R6-1: E rows, row R6: w  (PAIR: of the half, see R6h)
   TC_STAMP(blockIdx.x == 0 && blockIdx.y == 20 && threadIdx.x == 0, 7);
-  const bool packed = (R6 + 2 <= 64);
+  const bool packed = !PAIR && (R6 + 2 <= 64);          // two PIXEL halves of a 64-pixel chunk in operand rows 0..63 / 64..127
+  const bool two_halves = PAIR || packed;                // operand rows 64..127 carry a second set of lines
   const int nhalf = packed ? 2 : 1;
   const int cpx = 32 * nhalf;                            // pixels per chunk
   const int nchunks = (px_end - px_begin + cpx - 1) / cpx;
-  const int N = packed ? 128 : ((R6 + 1 + 15) & ~15);    // MMA N
+  const int N = two_halves ? 128 : ((R6 + 1 + 15) & ~15);    // MMA N
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t op_base = smem_u32(smem);               // [stage][hi|lo][128 rows][128 B], 1024-byte aligned tiles
@@ -869,7 +900,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
   uint64_t* done = acc_empty + kTcAccSlots;              // every MMA has completed
   uint32_t* tmem_base_smem = reinterpret_cast<uint32_t*>(done + 2);
 
-  if (tid < 128) s_gidx[tid] = (tid < R6) ? s_pose[tid / 6] * 6 + (tid % 6) : (tid == R6 ? -1 : -2);
+  if (tid < 128) {
+    if (PAIR) {                                          // operand row -> index in the reduced system, per half
+      const int hfx = tid >> 6, ln = tid & 63, R6x = hfx ? R6b : R6a, row0 = kPairTileRows * (hfx ? tb : ta);
+      s_gidx[tid] = (ln < R6x) ? s_pose[row0 + ln / 6] * 6 + (ln % 6) : (ln == R6x ? -1 : -2);
+    } else s_gidx[tid] = (tid < R6) ? s_pose[tid / 6] * 6 + (tid % 6) : (tid == R6 ? -1 : -2);
+  }
   if (tid == 0) {
     for (int s = 0; s < kTcOpStages; s++) { mbar_init(full + s, kTcProducers / 32); mbar_init(empty + s, 1); }
     for (int s = 0; s < kTcAccSlots; s++) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kTcProducers / 32); }
@@ -935,13 +971,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int li = 4 * i + (lane >> 3), piece = lane & 7;
-      const int hf = packed ? (li >> 3) : 0, line = warp + 8 * (packed ? (li & 7) : li);
+      const int hf = two_halves ? (li >> 3) : 0, line = warp + 8 * (two_halves ? (li & 7) : li);
+      const int R6x = PAIR ? (hf ? R6b : R6a) : R6, row0 = PAIR ? kPairTileRows * (hf ? tb : ta) : 0;
       // slots without a line copy zero bytes (cp.async zero-fills) into their unused slab row: no branch in the copy loop
       src[i] = Cin; pxo[i] = 1 << 30;
       dst[i] = raw_base + warp * 2048 + li * 128 + piece * 16;
-      if (line <= R6) {
-        const float* base = (line < R6) ? s_ptr[line / 6] + (size_t)(line % 6) * HW : win + (size_t)m * HW;
-        pxo[i] = hf * 32 + piece * 4;
+      if (line <= R6x) {
+        const float* base = (line < R6x) ? s_ptr[row0 + line / 6] + (size_t)(line % 6) * HW : win + (size_t)m * HW;
+        pxo[i] = (packed ? hf * 32 : 0) + piece * 4;
         src[i] = base + pxo[i];
       }
     }
@@ -951,9 +988,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
     const int q = warp & 3, half_w = warp >> 2;
     const int row = q * 32 + lane;
     const int lrow = packed ? (row & 63) : row;                     // line of this row
-    const int lq = packed ? (q & 1) : q;                            // 32-row group inside the half
+    const int lq = two_halves ? (q & 1) : q;                        // 32-row group inside the half
     const int ncb = packed ? 1 : 2;
     const int cb0 = packed ? ((q >> 1) * 64 + half_w * 32) : half_w * 32;
+    const int R6q = PAIR ? ((q >> 1) ? R6b : R6a) : R6;             // lines of this row's half
+    // PAIR: which of this thread's two column blocks are wanted: rows of tile a only need S_aa (block 0, if this CTA emits it);
+    // rows of tile b need S_ba (block 0) and S_bb (block 1, if emitted)
+    const bool need0 = !PAIR || ((q >> 1) ? true : emit_a);
+    const bool need1 = !PAIR || ((q >> 1) ? emit_b : false);
     float acc[2][32];
 #pragma unroll
     for (int h = 0; h < 2; h++)
@@ -966,7 +1008,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int cb = cb0 + h * 64;
-        if (h < ncb && cb < N && lq * 32 < R6) {                     // warp-uniform: groups without live rows skip the TMEM read
+        if (h < ncb && cb < N && lq * 32 < R6q && (h ? need1 : need0)) {     // warp-uniform: groups without live rows skip the TMEM read
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128 + cb), r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -1002,9 +1044,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       const int li = 4 * i + (lane >> 3);
-      const int hf = packed ? (li >> 3) : 0, line = warp + 8 * (packed ? (li & 7) : li);
+      const int hf = two_halves ? (li >> 3) : 0, line = warp + 8 * (two_halves ? (li & 7) : li);
       const uint32_t rr = (uint32_t)(hf * 64 + line);
-      live[i] = line <= R6;
+      live[i] = line <= (PAIR ? (hf ? R6b : R6a) : R6);
       op_off[i] = rr * 128 + (((uint32_t)piece ^ (rr & 7u)) << 4);
     }
     auto load_c4 = [&](int c, int hf) -> float4 {          // C of this thread's four pixels in half hf of chunk c (0 beyond the range)
@@ -1069,7 +1111,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int cb = cb0 + h * 64;
-      if (h < ncb && cb < N && lq * 32 <= R6) {
+      if (h < ncb && cb < N && lq * 32 <= R6q) {                     // PAIR: all four blocks of G (the lower-left block needs G^T from the upper right)
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(3 * 128 + cb), r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -1080,13 +1122,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
     asm volatile("bar.sync 1, %0;" ::"n"(kTcProducers) : "memory");
 
     // ================= epilogue: lower triangle of S (and the rhs column) into the reduced system =================
-    const int gr = (lrow < R6) ? s_gidx[lrow] : -2;
+    const int gr = PAIR ? s_gidx[row] : ((lrow < R6) ? s_gidx[lrow] : -2);
     if (gr >= 0) {
       const int cofs = packed ? (row & 64) : 0;                     // first operand column of this row's half
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int cb = cb0 + h * 64;
-        if (h < ncb && cb < N) {
+        if (h < ncb && cb < N && (h ? need1 : need0)) {
+          const bool cross = PAIR && ((row >> 6) != (cb >> 6));     // lower-left block S_ba: every unordered row pair appears once
 #pragma unroll
           for (int j = 0; j < 32; j++) {
             const int col = cb + j;
@@ -1094,7 +1137,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
             if (gc == -2) continue;
             const float g = lds_f32(op_base + (uint32_t)(row * kTcCxStride + col) * 4) + lds_f32(op_base + (uint32_t)(col * kTcCxStride + row) * 4);
             const double v = -(double)(acc[h][j] + g);
-            if (gc >= 0) {
+            if (cross) {
+              if (gc < 0) continue;                                 // the rhs comes from the diagonal blocks
+              if (gr > gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
+              else if (gr < gc) atomicAdd(&Hsys[(size_t)gc * n + gr], v);
+              else atomicAdd(&Hsys[(size_t)gr * n + gr], 2.0 * v);  // two different rows with the same pose: (r,c) and (c,r) land on one entry
+            } else if (gc >= 0) {
               if (gr >= gc) atomicAdd(&Hsys[(size_t)gr * n + gc], v);
             } else {
               atomicAdd(&bsys[gr], v);
@@ -1304,20 +1352,30 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
     if (!attr_set) {
       DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur gemm smem attr");
       DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2), "schur smem attr");
-      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem), "schur tc smem attr");
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem), "schur tc smem attr");
+      DBA_CHECK_CUDA(cudaFuncSetAttribute(ba_schur_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmem), "schur tc pair smem attr");
       attr_set = true;
     }
     // frames with at most 21 rows go to the tensor cores (needs 16-byte aligned pixel rows); DBA_SCHUR_SIMT=1 keeps the CUDA-core path
     static const bool force_simt = (getenv("DBA_SCHUR_SIMT") != nullptr && getenv("DBA_SCHUR_SIMT")[0] == '1');
     const bool use_tc = (HW % 4 == 0) && !force_simt;
+    int pair_rows_max = kTcRowsMax;                  // frames with more rows than this go to the SIMT kernel
     if (use_tc) {
       const int tiles64 = (HW + 63) / 64;
       const int chunks_tc = std::max(1, std::min(tiles64, (148 + eff_frames / 2) / eff_frames));     // one CTA per SM
       const int px_per_cta_tc = ((tiles64 + chunks_tc - 1) / chunks_tc) * 64;
       const int gx_tc = (HW + px_per_cta_tc - 1) / px_per_cta_tc;
-      ba_schur_tc_kernel<<<dim3(gx_tc, a->n_frames, 1), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+      ba_schur_tc_kernel<false><<<dim3(gx_tc, a->n_frames, 1), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta_tc, WS(float, L.off_Eij),
                                                            WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+      // frames with 22..100 rows (dense graphs, edge-sharded ranks): tile pairs over gridDim.z, whole pixel range per CTA; CTAs of
+      // frames outside that range (and pair indices beyond a frame's count) exit after the row-list build.  DBA_SCHUR_PAIR=0: SIMT kernel.
+      static const bool no_pair = (getenv("DBA_SCHUR_PAIR") != nullptr && getenv("DBA_SCHUR_PAIR")[0] == '0');
+      if (!no_pair)
+        ba_schur_tc_kernel<true><<<dim3(1, a->n_frames, kPairGridZ), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+                                                           WS(int, L.off_edgeidx), HW, a->t0, L.P, ((HW + 31) / 32) * 32, WS(float, L.off_Eij),
+                                                           WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+      pair_rows_max = no_pair ? kTcRowsMax : kPairRowsMax;
     } else {
       ba_schur_small_kernel<<<dim3(gx1, a->n_frames, 1), kSgThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta1, WS(float, L.off_Eij),
@@ -1325,7 +1383,7 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
     }
     DBA_CHECK_LAUNCH("ba_schur<single>");
     ba_schur_gemm_kernel<<<dim3(gx2, a->n_frames, zsplit2), kSgThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
-                                                                         WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta2, use_tc ? kTcRowsMax : kSgRows, WS(float, L.off_Eij),
+                                                                         WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta2, use_tc ? pair_rows_max : kSgRows, WS(float, L.off_Eij),
                                                                          WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
     DBA_CHECK_LAUNCH("ba_schur<multi>");
   }

@@ -148,3 +148,23 @@ def test_ba_every_schur_kernel_matches_oracle(backends):
     oracle.ba(P64, D64, s["intrinsics"], s["disps_sens"], s["targets"], s["weights"], s["eta"], s["ii"], s["jj"], s["t0"], s["t1"], 2,
               s["lm"], s["ep"], False, dtype=torch.float64)
     assert rel_err(P, P64, floor=1.0) < 1e-4 and rel_err(D, D64, floor=1.0) < 1e-4
+
+
+@pytest.mark.parametrize("N,res", [(40, (24, 32)), (30, (48, 64))])
+def test_ba_dense_graph_pair_mode_matches_oracle(backends, N, res):
+    """complete directed graphs (every frame has N-1 out-edges -> N rows per depth frame, 3-4 row tiles): every frame takes the tensor-core
+    PAIR mode of the Schur kernel -- the shape an edge-sharded rank of the 8-GPU run sees.  Includes duplicated edges whose two rows
+    fall into different tiles (the doubled-entry rule)."""
+    ii = [i for i in range(N) for j in range(N) if i != j]
+    jj = [j for i in range(N) for j in range(N) if i != j]
+    ii += [3, 3, 7]; jj += [N - 1, N - 2, N - 1]                       # duplicates: same (source, target) as rows of the first and the last tile
+    ht, wd = res
+    s = synth.make_scene(dict(E=len(ii), N=N, ht=ht, wd=wd, stereo=False, itrs=2, lm=1e-4, ep=0.1, graph=(ii, jj)), seed=2)
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    P, D = s["poses"].to(dev), s["disps"].to(dev)
+    args = [s[k].to(dev) for k in ("intrinsics", "disps_sens", "targets", "weights", "eta", "ii", "jj")]
+    backends.ba(P, D, *args, s["t0"], s["t1"], 2, s["lm"], s["ep"], False)
+    P64, D64 = s["poses"].double(), s["disps"].double()
+    oracle.ba(P64, D64, s["intrinsics"], s["disps_sens"], s["targets"], s["weights"], s["eta"], s["ii"], s["jj"], s["t0"], s["t1"], 2,
+              s["lm"], s["ep"], False, dtype=torch.float64)
+    assert rel_err(P, P64, floor=1.0) < 1e-4 and rel_err(D, D64, floor=1.0) < 1e-4, (rel_err(P, P64, floor=1.0), rel_err(D, D64, floor=1.0))
