@@ -9,12 +9,10 @@
 //     TRSM of the column-k tiles (one warp per tile, lane = row, forward substitution against L_kk in shared memory)
 //       -- cluster barrier --
 //     trailing update A_ij -= L_ik L_jk^T: one warp per tile with an 8x4 register block per lane (operands staged in the
-//     warp's padded shared-memory slabs, coalesced global I/O).
-//     CRITICAL CHAIN: the next panel needs potrf(k+1), which needs tile (k+1,k), which needs potrf(k).  Warp 0 of CTA 0 runs exactly
-//     that chain -- TRSM of tile (k+1,k), T_{k+1,k+1} -= X X^T in registers, potrf (rows in registers, pivot column broadcast through
-//     shared memory) -- back to back with no CTA- or cluster-wide synchronisation inside (it arrives at barrier 1 right after its
-//     TRSM and only waits for it after the potrf: split-phase cluster barrier), while the other 127 warps do the remaining TRSMs and
-//     all other trailing updates; a spare warp inverts L_kk for the backward pass
+//     warp's padded shared-memory slabs, coalesced global I/O).  The NEXT diagonal tile is on the critical path, so CTA 0
+//     updates it with all 256 threads and its warp 0 factors it immediately (rows in registers, the pivot column is
+//     broadcast through shared memory) while every other warp of the cluster works on the remaining tiles; a spare
+//     warp inverts L_kk for the backward pass
 //       -- cluster barrier --
 // i.e. two hardware cluster barriers per panel instead of kernel launches or grid-wide syncs.
 // ENVELOPE: the reduced pose system of a sliding-window / proximity factor graph is block banded (pose a couples to pose b only
@@ -44,7 +42,6 @@ constexpr int kCholWarps = kCholThreads / 32;
 
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define CHOL_STAMP(slot) do { if (p.timing && cta == 0 && tid == 0) p.timing[(slot)] = gtimer(); } while (0)
-#define CHOL_STAMP_W(slot) do { if (p.timing && cta == 0 && tid == 32) p.timing[(slot)] = gtimer(); } while (0)   // a worker warp of CTA 0
 __device__ __forceinline__ double ldcg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ void stcg(double* p, double v) { __stcg(p, v); }
 
@@ -281,12 +278,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     __syncthreads();
     const int nact = envelope ? s_nact : (nt - k);       // >= 1: the rhs row
     CHOL_STAMP(8 + 8 * k + 0);
-    const int rem = nt - k - 1;                       // remaining tile columns
-    const int m1 = nact - 1;                          // active rows without the rhs row
-    // row k+1 inside the envelope of panel k?  Then tile (k+1,k) is task 0 of the TRSM list and belongs to the critical chain below.
-    const bool diag_active = envelope ? (m1 >= 1 && s_act[0] == k + 1) : (rem >= 1);
-    const int t_first = diag_active ? 1 : 0;          // first TRSM task of the worker warps
-    auto trsm_tile = [&](int i, double (&a)[kT]) {    // one warp: tile (i,k) <- tile (i,k) L_kk^-T, result also left in s_A[warp] (row-major)
+    // ---- TRSM: tiles (i,k) of the active rows (tile row nt is the right-hand side)
+    for (int ta = gw; ta < nact; ta += nwarps) {
+      const int i = envelope ? s_act[ta] : k + 1 + ta;
+      double a[kT];
       double* tile = L + (size_t)(i * kT) * ld + k * kT;
 #pragma unroll
       for (int r = 0; r < kT; r++) s_A[warp][r][lane] = ldcg(tile + (size_t)r * ld + lane);     // coalesced rows, all 32 loads in flight
@@ -308,83 +303,61 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
 #pragma unroll 8
       for (int r = 0; r < kT; r++) stcg(tile + (size_t)r * ld + lane, s_A[warp][r][lane]);
       __syncwarp();
-    };
-    if (gw == 0) {
-      // ================= critical chain (one warp, no CTA- or cluster-wide synchronisation inside): TRSM of tile (k+1,k), the update
-      // of the next diagonal tile with it, and that tile's factorisation.  The next panel cannot start before potrf(k+1); everything
-      // else of this panel (the other TRSMs, the trailing updates) runs beside this chain on the other 127 warps.
-      double tt[kT];
+    }
+    CHOL_STAMP(8 + 8 * k + 1);
+    cluster.sync();
+    CHOL_STAMP(8 + 8 * k + 2);
+    // ---- trailing update with panel k
+    const int rem = nt - k - 1;                       // remaining tile columns
+    const int m1 = nact - 1;                          // active rows without the rhs row
+    const int ntri = m1 * (m1 + 1) / 2;
+    const int ntasks = ntri + m1;                     // tiles (i,j) of active rows, j <= i < nt, plus the rhs row tiles (nt,j)
+    // task 0 = tile (k+1,k+1) when row k+1 is active: CTA 0 updates + factors it below; otherwise that tile needs no update (CTA 0 still
+    // factors it) and task 0 is an ordinary tile of the workers
+    const bool diag_active = envelope ? (m1 >= 1 && s_act[0] == k + 1) : (rem >= 1);
+    if (cta == 0 && rem >= 1) {
+      // next diagonal tile (task 0): all 256 threads update it, warp 0 factors it
+      const double* At = L + (size_t)((k + 1) * kT) * ld + k * kT;
       double* Ct = L + (size_t)((k + 1) * kT) * ld + (k + 1) * kT;
-      if (rem >= 1) {
-#pragma unroll
-        for (int c = 0; c < kT; c++) tt[c] = ldcg(Ct + (size_t)lane * ld + c);        // prefetch this lane's row of tile (k+1,k+1)
+      for (int e = tid; e < kT * kT; e += kCholThreads) {
+        const int r = e >> 5, c = e & 31;
+        s_D[r][c] = ldcg(At + (size_t)r * ld + c);
+        s_T[r][c] = ldcg(Ct + (size_t)r * ld + c);
       }
-      if (diag_active) {
-        double a[kT];
-        trsm_tile(k + 1, a);
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");          // barrier 1 (split phase): tile (k+1,k) is published
-        // T -= X X^T: lane = row r, X[r][.] in registers, X[c][.] broadcast from the warp's slab; four columns at a time = four
-        // independent fp64 FMA chains (a dependent DFMA costs ~9 cycles, the warp issues one every 2)
+      __syncthreads();
+      {
+        const int r = tid >> 3, c0 = (tid & 7) * 4;
+        double acc[4] = {s_T[r][c0], s_T[r][c0 + 1], s_T[r][c0 + 2], s_T[r][c0 + 3]};
+#pragma unroll 8
+        for (int q = 0; q < kT; q++) {
+          const double ar = s_D[r][q];
 #pragma unroll
-        for (int c = 0; c < kT; c += 4) {
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-          for (int q = 0; q < kT; q++) {
-            const double aq = a[q];
-            s0 = fma(aq, s_A[warp][c][q], s0); s1 = fma(aq, s_A[warp][c + 1][q], s1);
-            s2 = fma(aq, s_A[warp][c + 2][q], s2); s3 = fma(aq, s_A[warp][c + 3][q], s3);
-          }
-          tt[c] -= s0; tt[c + 1] -= s1; tt[c + 2] -= s2; tt[c + 3] -= s3;
+          for (int jx = 0; jx < 4; jx++) acc[jx] -= ar * s_D[c0 + jx][q];
         }
-      } else {
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-      }
-      if (rem >= 1) {
-        if (p.timing && lane == 0) p.timing[8 + 8 * k + 5] = gtimer();
-        double rd;
-        if (!warp_potrf(tt, lane, s_col, rd) && lane == 0) *p.fail = 1;
-        if (p.timing && lane == 0) p.timing[8 + 8 * k + 6] = gtimer();
+        __syncthreads();
 #pragma unroll
-        for (int c = 0; c < kT; c++) stcg(Ct + (size_t)lane * ld + c, (c <= lane) ? tt[c] : 0.0);
+        for (int jx = 0; jx < 4; jx++) s_T[r][c0 + jx] = acc[jx];
+      }
+      __syncthreads();
+      if (warp == 0) {
+        if (p.timing && lane == 0) p.timing[8 + 8 * k + 5] = gtimer();
+        double a[kT], rd;
+#pragma unroll
+        for (int c = 0; c < kT; c++) a[c] = s_T[lane][c];
+        if (!warp_potrf(a, lane, s_col, rd) && lane == 0) *p.fail = 1;
+        if (p.timing && lane == 0) p.timing[8 + 8 * k + 6] = gtimer();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < kT; c++) s_T[lane][c] = (c <= lane) ? a[c] : 0.0;
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < kT; r++) stcg(Ct + (size_t)r * ld + lane, s_T[r][lane]);
         stcg(p.rdiag + (k + 1) * kT + lane, rd);
       }
-      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");               // barrier 1 complete (long since)
-    } else {
-      const int nwork = nwarps - 2;                     // worker warps 1 .. nwarps-2; the last warp only inverts L_kk (below)
-      const bool worker = gw < nwarps - 1;
-      if (!worker) {
-        // inverse of L_kk (for the backward substitution): lane j owns column j.  A 32-step dependent chain, so it gets a warp of its
-        // own: it arrives at barrier 1 at once (it publishes nothing the trailing updates need) and works beside the TRSMs and updates
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        double xcol[kT];
-#pragma unroll
-        for (int i = 0; i < kT; i++) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int m = 0; m < i; m++) sacc += (m >= lane) ? s_Lkk[i][m] * xcol[m] : 0.0;
-          xcol[i] = (i == lane) ? s_rdiag[i] : ((i > lane) ? -sacc * s_rdiag[i] : 0.0);
-        }
-#pragma unroll
-        for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-      }
-      // ---- TRSM of the other active rows (tile row nt is the right-hand side), spread over the worker warps
-      for (int ta = t_first + gw - 1; worker && ta < nact; ta += nwork) {
-        const int i = envelope ? s_act[ta] : k + 1 + ta;
-        double a[kT];
-        trsm_tile(i, a);
-      }
-      CHOL_STAMP_W(8 + 8 * k + 1);
-      if (worker) {
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");              // barrier 1: every TRSM'd tile of panel k is visible
-      }
-      CHOL_STAMP_W(8 + 8 * k + 2);
-      // ---- trailing update with panel k: tiles (i,j) of active rows, j <= i < nt, plus the rhs row tiles (nt,j); the next diagonal
-      // tile (task 0 when row k+1 is active) belongs to the chain warp
-      const int ntri = m1 * (m1 + 1) / 2;
-      const int ntasks = ntri + m1;
-      for (int t = t_first + gw - 1; worker && t < ntasks; t += nwork) {
+    }
+    // remaining tiles: every warp of the cluster except the factoring one
+    if (gw != 0) {
+      for (int t = (diag_active ? 1 : 0) + gw - 1; t < ntasks; t += nwarps - 1) {
         int i, j;
         if (t < ntri) {
           int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
@@ -397,7 +370,20 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
                          s_A[warp], s_B[warp]);
       }
     }
-    CHOL_STAMP_W(8 + 8 * k + 3);
+    CHOL_STAMP(8 + 8 * k + 3);
+    // inverse of L_kk (for the backward substitution) by the last warp of the cluster: lane j owns column j
+    if (gw == nwarps - 1) {
+      double xcol[kT];
+#pragma unroll
+      for (int i = 0; i < kT; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < i; m++) s += (m >= lane) ? s_Lkk[i][m] * xcol[m] : 0.0;
+        xcol[i] = (i == lane) ? s_rdiag[i] : ((i > lane) ? -s * s_rdiag[i] : 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
+    }
     cluster.sync();
     CHOL_STAMP(8 + 8 * k + 4);
   }

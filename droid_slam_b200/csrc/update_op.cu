@@ -588,26 +588,42 @@ template <> struct Load2<float> {
 };
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const T* __restrict__ src, __half* __restrict__ dst, int C, int HW, int dst_stride, int cwrite) {
-  __shared__ uint32_t tile[64][33];                         // [pixel][channel pair]
-  const int e = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  __shared__ uint32_t tile[2][64][33];                      // [channel block][pixel][channel pair]
+  // a CTA moves TWO 64-channel blocks of a 64-pixel tile: 16 loads per thread are in flight before the first use, and a pixel's
+  // output row is one 256-byte run
+  const int e = blockIdx.z, p0 = blockIdx.x * 64;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const bool even = (HW & 1) == 0;                           // pixel pairs are 4 / 8-byte aligned when HW is even
+  float2 va[2][4], vb[2][4];
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int cp = w + 8 * k;                                // channel pair 0..31
-    const int c = c0 + 2 * cp, pp = p0 + 2 * lane;
-    float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-    if (c < C && pp < HW) a = Load2<T>::ld(src + ((size_t)e * C + c) * HW + pp, true, pp + 1 < HW, even);
-    if (c + 1 < C && pp < HW) b = Load2<T>::ld(src + ((size_t)e * C + c + 1) * HW + pp, true, pp + 1 < HW, even);
-    tile[2 * lane][cp] = pack2(a.x, b.x);
-    tile[2 * lane + 1][cp] = pack2(a.y, b.y);
+  for (int cbk = 0; cbk < 2; cbk++) {
+    const int c0 = (blockIdx.y * 2 + cbk) * 64;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int cp = w + 8 * k;                              // channel pair 0..31
+      const int c = c0 + 2 * cp, pp = p0 + 2 * lane;
+      va[cbk][k] = make_float2(0.f, 0.f); vb[cbk][k] = make_float2(0.f, 0.f);
+      if (c < C && pp < HW) va[cbk][k] = Load2<T>::ld(src + ((size_t)e * C + c) * HW + pp, true, pp + 1 < HW, even);
+      if (c + 1 < C && pp < HW) vb[cbk][k] = Load2<T>::ld(src + ((size_t)e * C + c + 1) * HW + pp, true, pp + 1 < HW, even);
+    }
   }
+#pragma unroll
+  for (int cbk = 0; cbk < 2; cbk++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int cp = w + 8 * k;
+      tile[cbk][2 * lane][cp] = pack2(va[cbk][k].x, vb[cbk][k].x);
+      tile[cbk][2 * lane + 1][cp] = pack2(va[cbk][k].y, vb[cbk][k].y);
+    }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int px = w + 8 * k, pp = p0 + px;
-    const int c = c0 + 2 * lane;
-    if (pp < HW && c < cwrite) *reinterpret_cast<uint32_t*>(dst + ((size_t)e * HW + pp) * dst_stride + c) = tile[px][lane];   // cwrite and strides are even
+#pragma unroll
+    for (int cbk = 0; cbk < 2; cbk++) {
+      const int c = (blockIdx.y * 2 + cbk) * 64 + 2 * lane;
+      if (pp < HW && c < cwrite) *reinterpret_cast<uint32_t*>(dst + ((size_t)e * HW + pp) * dst_stride + c) = tile[cbk][px][lane];   // cwrite and strides are even
+    }
   }
 }
 
@@ -919,7 +935,7 @@ extern "C" int dba_update_forward(const dba_update_args* a) {
   int* seg_edges = (int*)(ws + L.segedges);
 
   // ---- layout changes into channels-last f16 --------------------------------------------------------------------------
-  const dim3 tgrid128((HW + 63) / 64, 2, E);
+  const dim3 tgrid128((HW + 63) / 64, 1, E);
   const __half* H;      // hidden state, channels-last [E][HW][128]
   if (a->net_layout == 1) H = (const __half*)a->net;
   else {
@@ -934,7 +950,7 @@ extern "C" int dba_update_forward(const dba_update_args* a) {
   else if (a->inp_dtype == DBA_F32) nchw_to_nhwc_kernel<float><<<tgrid128, 256, 0, st>>>((const float*)a->inp, X, 128, HW, 320, 128);
   else { set_error("invalid argument: inp dtype must be f16 or f32"); return DBA_ERR_INVALID; }
   {
-    const dim3 g((HW + 63) / 64, 4, E);
+    const dim3 g((HW + 63) / 64, 2, E);
     if (a->corr_dtype == DBA_F16) nchw_to_nhwc_kernel<__half><<<g, 256, 0, st>>>((const __half*)a->corr, Cc, 196, HW, 200, 200);
     else if (a->corr_dtype == DBA_F32) nchw_to_nhwc_kernel<float><<<g, 256, 0, st>>>((const float*)a->corr, Cc, 196, HW, 200, 200);
     else { set_error("invalid argument: corr dtype must be f16 or f32"); return DBA_ERR_INVALID; }
