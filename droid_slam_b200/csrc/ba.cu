@@ -29,7 +29,7 @@ constexpr int kBuildThreads = 256;
 constexpr int kEdgeBatch = 16;     // edges whose transforms / partial sums live in shared memory at once
 
 struct Layout {
-  size_t off_hdr, off_frame2k, off_kx, off_rowptr, off_edgeidx, off_sys, off_L, off_dx, off_Eij, off_C, off_w, off_Ei, total;
+  size_t off_hdr, off_frame2k, off_kx, off_rowptr, off_edgeidx, off_big, off_sys, off_L, off_dx, off_Eij, off_C, off_w, off_Ei, total;
   int P, n;
 };
 
@@ -46,6 +46,7 @@ __host__ inline Layout make_layout(int N, int E, int ht, int wd, int t0, int t1)
   L.off_kx = o;       o = align_up(o + (size_t)(N + 1) * sizeof(int), 256);
   L.off_rowptr = o;   o = align_up(o + (size_t)(N + 2) * sizeof(int), 256);
   L.off_edgeidx = o;  o = align_up(o + (size_t)(E + 1) * sizeof(int), 256);
+  L.off_big = o;      o = align_up(o + (size_t)(N + 1) * sizeof(int), 256);     // depth frames with more than 21 possible rows (pair-mode Schur)
   L.off_sys = o;      o = align_up(o + ((size_t)L.n * L.n + L.n) * sizeof(double), 256);
   L.off_L = o;        o = align_up(o + chol_workspace_bytes(L.n), 256);
   L.off_dx = o;       o = align_up(o + (size_t)(L.n + 6) * sizeof(float), 256);
@@ -59,7 +60,7 @@ __host__ inline Layout make_layout(int N, int E, int ht, int wd, int t0, int t1)
 }
 
 // header words
-enum { HDR_STATUS = 0, HDR_M = 1, HDR_CHOL_FAIL = 2 };
+enum { HDR_STATUS = 0, HDR_M = 1, HDR_CHOL_FAIL = 2, HDR_NBIG = 3 };
 enum { ST_BAD_INDEX = 1, ST_ETA_ROWS = 2, ST_CHOL_FAIL = 4, ST_DEGREE = 8 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -67,7 +68,7 @@ enum { ST_BAD_INDEX = 1, ST_ETA_ROWS = 2, ST_CHOL_FAIL = 4, ST_DEGREE = 8 };
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) ba_prepare_kernel(const int64_t* __restrict__ ii, const int64_t* __restrict__ jj, int E, int N,
                                                           int t0, int t1, int eta_rows, int* __restrict__ hdr,
-                                                          int* __restrict__ frame2k, int* __restrict__ kx, int* __restrict__ rowptr) {
+                                                          int* __restrict__ frame2k, int* __restrict__ kx, int* __restrict__ rowptr, int* __restrict__ big) {
   __shared__ int s_scan[1024];
   __shared__ int s_carry;
   const int tid = threadIdx.x;
@@ -135,6 +136,27 @@ __global__ void __launch_bounds__(1024) ba_prepare_kernel(const int64_t* __restr
     if (tid == blockDim.x - 1) s_carry += s_scan[tid];
     __syncthreads();
   }
+  // depth frames that can have more than kTcRowsMax (21) rows = out-degree + 1: the pair-mode Schur launch only visits these
+  // (ascending order; there are at most E / 21 of them, which is what sizes that launch's grid)
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < M; base += blockDim.x) {
+    const int m = base + tid;
+    const int flag = (m < M && rowptr[m + 1] - rowptr[m] + 1 > 21) ? 1 : 0;
+    s_scan[tid] = flag;
+    __syncthreads();
+    for (int off = 1; off < (int)blockDim.x; off <<= 1) {
+      int v = (tid >= off) ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    if (flag) big[s_carry + s_scan[tid] - 1] = m;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry += s_scan[tid];
+    __syncthreads();
+  }
+  if (tid == 0) hdr[HDR_NBIG] = s_carry;
 }
 
 // stable placement of every edge inside its source frame's segment: rank = #earlier edges with the same source.
@@ -836,8 +858,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) ba_schur_tc_kernel(
     const int64_t* __restrict__ jj, int* __restrict__ hdr, const int* __restrict__ kx, const int* __restrict__ rowptr,
     const int* __restrict__ edgeidx, int HW, int t0, int P, int px_per_cta,
     const float* __restrict__ Eij, const float* __restrict__ Cin, const float* __restrict__ win, const float* __restrict__ Eiin,
-    double* __restrict__ Hsys, double* __restrict__ bsys) {
-  const int m = blockIdx.y;
+    double* __restrict__ Hsys, double* __restrict__ bsys, const int* __restrict__ big) {
+  if (PAIR && (int)blockIdx.y >= hdr[HDR_NBIG]) return;          // PAIR: blockIdx.y runs over the list of high-degree depth frames
+  const int m = PAIR ? big[blockIdx.y] : blockIdx.y;
   if (m >= hdr[HDR_M]) return;
   const int ix = kx[m];
   const int e_begin = rowptr[m];
@@ -1306,7 +1329,7 @@ extern "C" int dba_ba_prepare(const dba_ba_args* a) {
   Layout L; int rc = check_ba_args(a, L); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)a->stream;
   ba_prepare_kernel<<<1, 1024, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, a->t0, a->t1, (a->motion_only || a->eta_by_frame) ? 1 : a->eta_rows,
-                                        WS(int, L.off_hdr), WS(int, L.off_frame2k), WS(int, L.off_kx), WS(int, L.off_rowptr));
+                                        WS(int, L.off_hdr), WS(int, L.off_frame2k), WS(int, L.off_kx), WS(int, L.off_rowptr), WS(int, L.off_big));
   DBA_CHECK_LAUNCH("ba_prepare");
   if (a->n_edges > 0) {
     ba_fill_csr_kernel<<<(a->n_edges + 7) / 8, 256, 0, st>>>(a->ii, a->jj, a->n_edges, a->n_frames, WS(int, L.off_frame2k),
@@ -1367,14 +1390,15 @@ extern "C" int dba_ba_build(const dba_ba_args* a) {
       const int gx_tc = (HW + px_per_cta_tc - 1) / px_per_cta_tc;
       ba_schur_tc_kernel<false><<<dim3(gx_tc, a->n_frames, 1), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, px_per_cta_tc, WS(float, L.off_Eij),
-                                                           WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+                                                           WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys, WS(int, L.off_big));
       // frames with 22..100 rows (dense graphs, edge-sharded ranks): tile pairs over gridDim.z, whole pixel range per CTA; CTAs of
       // frames outside that range (and pair indices beyond a frame's count) exit after the row-list build.  DBA_SCHUR_PAIR=0: SIMT kernel.
       static const bool no_pair = (getenv("DBA_SCHUR_PAIR") != nullptr && getenv("DBA_SCHUR_PAIR")[0] == '0');
-      if (!no_pair)
-        ba_schur_tc_kernel<true><<<dim3(1, a->n_frames, kPairGridZ), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
+      const int max_big = std::min(a->n_frames, a->n_edges / kTcRowsMax);     // a frame with 22+ rows has 21+ out-edges
+      if (!no_pair && max_big > 0)
+        ba_schur_tc_kernel<true><<<dim3(1, max_big, kPairGridZ), kTcThreads, kTcSmem, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
                                                            WS(int, L.off_edgeidx), HW, a->t0, L.P, ((HW + 31) / 32) * 32, WS(float, L.off_Eij),
-                                                           WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys);
+                                                           WS(float, L.off_C), WS(float, L.off_w), WS(float, L.off_Ei), Hsys, bsys, WS(int, L.off_big));
       pair_rows_max = no_pair ? kTcRowsMax : kPairRowsMax;
     } else {
       ba_schur_small_kernel<<<dim3(gx1, a->n_frames, 1), kSgThreads, smem2, st>>>(a->jj, WS(int, L.off_hdr), WS(int, L.off_kx), WS(int, L.off_rowptr),
