@@ -752,6 +752,7 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # unset: NCCL prints its version banner on stdout next to the one JSON line; a caller's own setting (e.g. INFO) is kept
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         if args.impl == "reference":

@@ -18,6 +18,7 @@
 //     skip-semantics slow path.
 //   * no memset of the output (the reference needs torch::zeros + 4 global RMWs per element).
 #include "common.cuh"
+#include <type_traits>
 
 namespace dba {
 
@@ -202,11 +203,15 @@ __device__ __forceinline__ void align_row_f16(const uint4& A, const uint4& B, in
 // tiles ([h2/4][w2/8][4][8], one 64-byte DRAM atom per tile, written by corr_volume_pyramid's tiled mode): the 8x8 window then
 // touches 5.2 atoms on average instead of 8-10 (a 16-byte window row at arbitrary alignment costs a whole atom in the row-major
 // plane); the arithmetic and therefore every output bit is the same.
-template <bool TILED>
-__device__ __forceinline__ void corr_pixel_f16_r3(const __half* __restrict__ plane, __half* __restrict__ out_px, size_t out_stride,
+// T16 = __half (reference arithmetic: product and sum rounded in f16, two taps per half2 instruction) or __nv_bfloat16 (extension:
+// fp32 FMA chain on the bf16 inputs, rounded once -- the same function as the generic bf16 path, with the vector loads of the f16 one)
+template <bool TILED, typename T16 = __half>
+__device__ __forceinline__ void corr_pixel_f16_r3(const T16* __restrict__ plane, T16* __restrict__ out_px, size_t out_stride,
                                                   float x0, float y0, int h2, int w2) {
+  constexpr bool kHalf = sizeof(T16) == 2 && std::is_same<T16, __half>::value;
   if (!(isfinite(x0) && isfinite(y0))) {   // exact reference semantics for NaN/inf coordinates (slow path)
-    corr_pixel_generic<__half, TILED>(plane, out_px, out_stride, x0, y0, h2, w2, 3);
+    if constexpr (TILED && !kHalf) return;                                       // (tiled planes exist for f16 only)
+    else corr_pixel_generic<T16, TILED>(plane, out_px, out_stride, x0, y0, h2, w2, 3);
     return;
   }
   const float fxf = floorf(x0), fyf = floorf(y0);
@@ -222,15 +227,16 @@ __device__ __forceinline__ void corr_pixel_f16_r3(const __half* __restrict__ pla
   for (int b = 0; b < 8; b++) {
     const int y1 = y1s + b;
     const bool rowok = (unsigned)y1 < (unsigned)h2;
-    const __half* row = TILED ? plane + ((size_t)(y1 >> 2) * tpr + (a0 >> 3)) * 32 + (y1 & 3) * 8 : plane + (size_t)y1 * w2 + a0;
+    const T16* row = TILED ? plane + ((size_t)(y1 >> 2) * tpr + (a0 >> 3)) * 32 + (y1 & 3) * 8 : plane + (size_t)y1 * w2 + a0;
     A[b] = make_uint4(0, 0, 0, 0); B[b] = make_uint4(0, 0, 0, 0);
     if (rowok && okA) A[b] = ldg_nc_v4(row);
     if (rowok && okB) B[b] = ldg_nc_v4(row + (TILED ? 32 : 8));
   }
-  const __half2 w00 = __half2half2(__float2half_rn((1.0f - dx) * (1.0f - dy)));
-  const __half2 w01 = __half2half2(__float2half_rn((1.0f - dx) * dy));
-  const __half2 w10 = __half2half2(__float2half_rn(dx * (1.0f - dy)));
-  const __half2 w11 = __half2half2(__float2half_rn(dx * dy));
+  const float f00 = (1.0f - dx) * (1.0f - dy), f01 = (1.0f - dx) * dy, f10 = dx * (1.0f - dy), f11 = dx * dy;
+  const __half2 w00 = __half2half2(__float2half_rn(f00));
+  const __half2 w01 = __half2half2(__float2half_rn(f01));
+  const __half2 w10 = __half2half2(__float2half_rn(f10));
+  const __half2 w11 = __half2half2(__float2half_rn(f11));
   const __half2 zero2 = __half2half2(__float2half_rn(0.f));
 
   uint32_t pa[4], ps[4], ca[4], cs[4], dummy;   // aligned / shifted-by-one-tap words of previous and current row
@@ -244,27 +250,37 @@ __device__ __forceinline__ void corr_pixel_f16_r3(const __half* __restrict__ pla
     cs[2] = __funnelshift_r(ca[2], ca[3], 16); cs[3] = ca[3] >> 16;
 #pragma unroll
     for (int k = 0; k < 4; k++) {   // lanes (i=2k, i=2k+1)
-      __half2 t = __hadd2_rn(zero2, __hmul2_rn(u32_as_h2(pa[k]), w00));   // tap (i  , j  )
-      t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(ca[k]), w01));               // tap (i  , j+1)
-      t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(ps[k]), w10));               // tap (i+1, j  )
-      t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(cs[k]), w11));               // tap (i+1, j+1)
-      out_px[(size_t)((2 * k) * 7 + j) * out_stride] = __low2half(t);
-      if (k < 3) out_px[(size_t)((2 * k + 1) * 7 + j) * out_stride] = __high2half(t);
+      if constexpr (kHalf) {
+        __half2 t = __hadd2_rn(zero2, __hmul2_rn(u32_as_h2(pa[k]), w00));   // tap (i  , j  )
+        t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(ca[k]), w01));               // tap (i  , j+1)
+        t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(ps[k]), w10));               // tap (i+1, j  )
+        t = __hadd2_rn(t, __hmul2_rn(u32_as_h2(cs[k]), w11));               // tap (i+1, j+1)
+        out_px[(size_t)((2 * k) * 7 + j) * out_stride] = __low2half(t);
+        if (k < 3) out_px[(size_t)((2 * k + 1) * 7 + j) * out_stride] = __high2half(t);
+      } else {                         // bf16 -> fp32 is a 16-bit shift; same tap order as the generic path
+        float lo = fmaf(__uint_as_float(pa[k] << 16), f00, 0.f), hi = fmaf(__uint_as_float(pa[k] & 0xffff0000u), f00, 0.f);
+        lo = fmaf(__uint_as_float(ca[k] << 16), f01, lo); hi = fmaf(__uint_as_float(ca[k] & 0xffff0000u), f01, hi);
+        lo = fmaf(__uint_as_float(ps[k] << 16), f10, lo); hi = fmaf(__uint_as_float(ps[k] & 0xffff0000u), f10, hi);
+        lo = fmaf(__uint_as_float(cs[k] << 16), f11, lo); hi = fmaf(__uint_as_float(cs[k] & 0xffff0000u), f11, hi);
+        out_px[(size_t)((2 * k) * 7 + j) * out_stride] = __float2bfloat16_rn(lo);
+        if (k < 3) out_px[(size_t)((2 * k + 1) * 7 + j) * out_stride] = __float2bfloat16_rn(hi);
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) { pa[k] = ca[k]; ps[k] = cs[k]; }
   }
 }
 
-__global__ void __launch_bounds__(128) corr_index_fwd_f16_r3_kernel(const __half* __restrict__ vol, const float* __restrict__ coords,
-                                                                    __half* __restrict__ out, long long total, int hw1, int h2, int w2) {
+template <typename T16>
+__global__ void __launch_bounds__(128) corr_index_fwd_f16_r3_kernel(const T16* __restrict__ vol, const float* __restrict__ coords,
+                                                                    T16* __restrict__ out, long long total, int hw1, int h2, int w2) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
   const int n = (int)(p / hw1);
   const int pin = (int)(p - (long long)n * hw1);
   const float x0 = coords[((size_t)n * 2 + 0) * hw1 + pin];
   const float y0 = coords[((size_t)n * 2 + 1) * hw1 + pin];
-  corr_pixel_f16_r3<false>(vol + (size_t)p * h2 * w2, out + (size_t)n * 49 * hw1 + pin, (size_t)hw1, x0, y0, h2, w2);
+  corr_pixel_f16_r3<false, T16>(vol + (size_t)p * h2 * w2, out + (size_t)n * 49 * hw1 + pin, (size_t)hw1, x0, y0, h2, w2);
 }
 
 // CorrBlock.__call__ (reference modules/corr.py:40-50) in ONE launch: all four pyramid levels of a pixel by one thread -- the
@@ -396,8 +412,13 @@ extern "C" int dba_corr_index_forward(const void* volume, const float* coords, v
   const int threads = 128;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
   if (radius == 3 && dtype == DBA_F16 && aligned && (w2 % 8) == 0 && h2 > 0) {
-    corr_index_fwd_f16_r3_kernel<<<blocks, threads, 0, st>>>((const __half*)volume, coords, (__half*)corr, total, hw1, h2, w2);
+    corr_index_fwd_f16_r3_kernel<__half><<<blocks, threads, 0, st>>>((const __half*)volume, coords, (__half*)corr, total, hw1, h2, w2);
     DBA_CHECK_LAUNCH("corr_index_forward(f16,r3)");
+    return DBA_OK;
+  }
+  if (radius == 3 && dtype == DBA_BF16 && aligned && (w2 % 8) == 0 && h2 > 0) {
+    corr_index_fwd_f16_r3_kernel<__nv_bfloat16><<<blocks, threads, 0, st>>>((const __nv_bfloat16*)volume, coords, (__nv_bfloat16*)corr, total, hw1, h2, w2);
+    DBA_CHECK_LAUNCH("corr_index_forward(bf16,r3)");
     return DBA_OK;
   }
   if (radius == 3 && dtype == DBA_F32 && aligned && (w2 % 4) == 0 && h2 > 0) {
