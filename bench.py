@@ -224,7 +224,17 @@ def run_ours(args, rank, world, dev):
     if args.collective == "auto":
         args.collective = "p2p" if 6 * (pb["t1"] - pb["t0"]) <= 1024 else "nccl"
     if world > 1 and args.collective == "p2p":
+        # every rank first agrees that symmetric memory can be tried at all, so that no rank enters the rendezvous collective alone
         try:
+            import torch.distributed._symmetric_memory as _symm  # noqa: F401
+            can = 1.0
+        except Exception:
+            can = 0.0
+        okc = torch.tensor([can], device=dev)
+        dist.all_reduce(okc, op=dist.ReduceOp.MIN)
+        try:
+            if float(okc) == 0.0:
+                raise RuntimeError("torch.distributed._symmetric_memory is not importable on every rank")
             p2p = sharded.P2PSystem(6 * (pb["t1"] - pb["t0"]), dev)
         except Exception as e:                       # no peer-mapped memory on this box: plain NCCL all-reduce of the pose system
             sys.stderr.write("[bench] rank %d: symmetric memory unavailable (%s); using the NCCL all-reduce path\n" % (rank, str(e)[:160]))
