@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -92,6 +93,10 @@ struct CholParams {
   double* Linv;      // [nt][32][32] inverses of the diagonal tiles
   double* rdiag;     // [nt*32] reciprocals of diag(L)
   int* first;        // [nt+1] envelope: first nonzero tile column of each tile row (rhs row nt: 0)
+  int* flags;        // (unused)
+  unsigned sleep_urgent, sleep_idle;   // resident-tile kernel: ns between polls of a warp on / off the critical path
+  int warm;                            // bit 1: the diagonal owner substitutes tile (j, j-1) itself (default; DBA_CHOL_FUSED_SUBST=0 turns it off)
+  double* Cs;                          // resident-tile kernel: [nt][32][32] tiles (j+1, j) BEFORE the substitution (for mode 2)
   int* fail;         // sticky flag: non-positive pivot
   float* x;          // [n] result (fp32 like the reference's dx)
   int n, nt;
@@ -419,10 +424,492 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
   }
 }
 
+
+// =====================================================================================================================================
+// Resident-tile dataflow variant for nt <= 14 (n <= 448: every frontend window, the 72-keyframe metric window).
+//
+// The barrier version above spends a panel on  L_kk reload -> TRSM -> cluster barrier -> trailing update -> cluster barrier.  Measured
+// (in-kernel %globaltimer): the arithmetic is ~3 us of that; the rest is synchronisation -- in particular every acquire (cluster barrier,
+// ld.acquire, fence) ends in CCTL.IVALL, after which the next global loads of the warp take ~3 us instead of ~0.3.
+// Here every lower tile (i,j) and every 32-entry piece of the right-hand side has ONE owner warp for the whole factorisation (105 + 14
+// tiles <= 128 warps of the 16-CTA cluster) and lives in that warp's registers.  An owner applies  C -= L_ik L_jk^T  for k = 0..j-1 as
+// soon as the two operand tiles exist, then finalises its tile (potrf on the diagonal, a substitution against L_jj below it) and writes it
+// to global memory once.  There are no flags, fences or barriers inside the factorisation: the data validates itself.  Every output
+// location is filled with a NaN bit pattern that no arithmetic produces before the (single) cluster barrier of the prologue, a double
+// is written with one 8-byte store, and a consumer simply re-reads a tile from L2 (ld.global.cg) until no element is the sentinel --
+// the scheme of NCCL's low-latency protocol, without spending bits on a flag.  The only serial path left is the true one,
+// potrf(k) -> tile (k+1,k) -> last update of (k+1,k+1) -> potrf(k+1), with one L2 round trip per hand-over.
+// Waits are bounded; a wait that expires marks the solve failed (dx = 0) instead of hanging.
+constexpr int kResMaxNt = 14;
+constexpr unsigned long long kSentinel = 0xFFF7DEADBEEF5A5Aull;
+
+
+__device__ __forceinline__ bool is_sentinel(double v) { return __double2hiint(v) == (int)(kSentinel >> 32); }   // arithmetic NaNs are canonical
+__device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)kSentinel); }
+
+// wait until the 32x32 tile at src is completely written, then stage it in the warp's padded slab.  false on time-out.
+// `urgent` (the consumer sits on the critical path): no probe stage, short back-off; otherwise a one-row probe with a long back-off so
+// that the ~100 waiting warps take neither issue slots nor L2 bandwidth from the working ones.
+__device__ __forceinline__ bool tile_fetch(const double* src, int ld, int lane, double (*slab)[kTP], unsigned sleep_ns, unsigned sleep_retry) {
+  int tries = 0;
+  while (true) {                                             // cheap probe: the row that is stored last
+    const double v = __ldcg(src + (size_t)(kT - 1) * ld + lane);
+    if (!__any_sync(0xffffffffu, is_sentinel(v))) break;
+    if (++tries > (1 << 19)) return false;
+    __nanosleep(sleep_ns);
+  }
+  for (tries = 0; tries < (1 << 19); tries++) {
+    double t[kT];
+#pragma unroll
+    for (int r = 0; r < kT; r++) t[r] = __ldcg(src + (size_t)r * ld + lane);
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < kT; r++) bad |= is_sentinel(t[r]);
+    if (!__any_sync(0xffffffffu, bad)) {
+#pragma unroll
+      for (int r = 0; r < kT; r++) slab[r][lane] = t[r];
+      __syncwarp();
+      return true;
+    }
+    __nanosleep(sleep_retry);
+  }
+  return false;
+}
+// the same for a 32-entry vector (a piece of y, the reciprocal diagonal of a tile): lane c receives entry c
+__device__ __forceinline__ bool vec_fetch(const double* src, int lane, double& out, unsigned sleep_ns) {
+  for (int tries = 0; tries < (1 << 20); tries++) {
+    const double v = __ldcg(src + lane);
+    if (!__any_sync(0xffffffffu, is_sentinel(v))) { out = v; return true; }
+    __nanosleep(sleep_ns);
+  }
+  out = 0.0;
+  return false;
+}
+
+// acc (8x4 per lane: rows 8rg+i, cols 4cg+jx) -= A * B^T with A, B 32x32 tiles already staged in the warp's padded slabs
+__device__ __forceinline__ void slab_mac(double (&acc)[8][4], const double (*sA)[kTP], const double (*sB)[kTP], int lane) {
+  const int rg = lane >> 3, cgp = lane & 7;
+#pragma unroll 4
+  for (int q = 0; q < kT; q++) {
+    double av[8], bv[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) av[i] = sA[8 * rg + i][q];
+#pragma unroll
+    for (int jx = 0; jx < 4; jx++) bv[jx] = sB[4 * cgp + jx][q];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int jx = 0; jx < 4; jx++) acc[i][jx] -= av[i] * bv[jx];
+  }
+}
+
+// one entry of the damped, padded working matrix straight from H / b (or from the peers' partial systems, summed in rank order)
+__device__ __forceinline__ size_t sys_index(int r, int c, int n, bool diag_tile) {
+  if (r < n && c < n) {
+    if (c <= r) return (size_t)r * n + c;
+    if (diag_tile) return (size_t)c * n + r;
+  }
+  return (size_t)-1;
+}
+
+#define RES_STAMP(col, slot) do { if (p.timing && lane == 0) p.timing[8 + 16 * (col) + (slot)] = gtimer(); } while (0)
+
+__global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int ncta = (int)cluster.num_blocks();
+  const int cta = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nt = p.nt, n = p.n;
+  const int ld = nt * kT;
+  double* __restrict__ L = p.L;
+  double* yrow = L + (size_t)(nt * kT) * ld;
+  const int world = p.peers.world;
+  const size_t nn = (size_t)n * n;
+
+  __shared__ double s_rd[kCholWarps][kT];
+  __shared__ double s_colb[kCholWarps][2 * kT];
+  __shared__ double s_vec[kT];
+  extern __shared__ double s_dyn[];
+  double (*s_A)[kT][kTP] = reinterpret_cast<double (*)[kT][kTP]>(s_dyn);
+  double (*s_B)[kT][kTP] = reinterpret_cast<double (*)[kT][kTP]>(s_dyn + (size_t)kCholWarps * kT * kTP);
+
+  // ---- prologue: wait for the peers' systems (multi-GPU), dense envelope for the backward pass
+  for (int i = cta * kCholThreads + tid; i <= nt; i += ncta * kCholThreads) p.first[i] = 0;
+  if (world > 1) {
+    __shared__ int s_timeout;
+    if (tid == 0) {
+      int bad = 0;
+      const unsigned long long want = p.peers.epoch_dev ? *p.peers.epoch_dev : p.peers.epoch;
+      for (int r = 0; r < world; r++) {
+        unsigned long long v = 0;
+        long long spins = 0;
+        do {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p.peers.flags + r) : "memory");
+        } while (v < want && ++spins < (1ll << 24));
+        if (v < want) bad = 1;
+      }
+      s_timeout = bad;
+    }
+    __syncthreads();
+    if (cta == 0 && tid == 0) *p.fail = s_timeout ? 2 : 0;
+  } else if (cta == 0 && tid == 0) *p.fail = 0;
+
+  // ---- tile of this warp.  The critical path runs through the diagonal tiles and the tiles right below them; they get CTAs of their own
+  //      (measured: a potrf takes 5.4 us next to seven warps doing trailing updates and 2.9 us on a quiet SM, a substitution 2.2 vs 1.0),
+  //      diagonal tiles first so that the potrf code stays in those SMs' instruction caches.  Every other tile and the right-hand side
+  //      pieces are dealt round-robin (column-major, so one column's tiles -- which become ready together -- sit on different SMs).
+  const int ntiles = nt * (nt + 1) / 2 + nt;
+  const int nchain = 2 * nt - 1;
+  const int chain_ctas = (nchain + kCholWarps - 1) / kCholWarps;
+  bool has_tile = false;
+  int i = 0, j = 0;
+  if (cta < chain_ctas) {
+    const int slot = cta * kCholWarps + warp;
+    if (slot < nt) { has_tile = true; i = j = slot; }
+    else if (slot < nchain) { has_tile = true; j = slot - nt; i = j + 1; }
+  } else {
+    int rem = (cta - chain_ctas) + (ncta - chain_ctas) * warp;       // index into the other tiles, column-major
+    if (rem < ntiles - nchain) {
+      has_tile = true;
+      while (true) {
+        const int cnt = (nt - 2 - j > 0 ? nt - 2 - j : 0) + 1;       // tiles (j+2 .. nt-1, j) and the right-hand side piece (nt, j)
+        if (rem < cnt) break;
+        rem -= cnt; j++;
+      }
+      const int below = (nt - 2 - j > 0 ? nt - 2 - j : 0);
+      i = (rem < below) ? j + 2 + rem : nt;
+    }
+  }
+  const int rg = lane >> 3, cgp = lane & 7;
+  double acc[8][4];
+  double y = 0.0;
+  if (has_tile && i < nt) {
+    // own tile from H (damping, identity padding, diagonal tiles kept fully symmetric) -- issued before the barrier below
+    double t[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+#pragma unroll
+      for (int jx = 0; jx < 4; jx++) {
+        const int r = i * kT + 8 * rg + a, c = j * kT + 4 * cgp + jx;
+        const size_t src = sys_index(r, c, n, i == j);
+        double v = (src == (size_t)-1 && r == c) ? 1.0 : 0.0;
+        if (src != (size_t)-1) {
+          if (world > 1) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              t[q] = 0.0;
+              if (q < world) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(t[q]) : "l"(p.peers.sys[q] + src) : "memory");
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+              if (q < world) v += t[q];
+          } else v = p.H[src];
+          if (r == c) v += p.ep + p.lm * v;
+        }
+        acc[a][jx] = v;
+      }
+    }
+    // sentinel over everything this warp will publish
+    double* tile = L + (size_t)(i * kT) * ld + j * kT;
+#pragma unroll 8
+    for (int r = 0; r < kT; r++) stcg(tile + (size_t)r * ld + lane, sentinel());
+    if (i == j + 1 && (p.warm & 2)) {
+#pragma unroll 8
+      for (int r = 0; r < kT; r++) stcg(p.Cs + ((size_t)j * kT + r) * kT + lane, sentinel());
+    }
+    if (i == j) {
+      stcg(p.rdiag + j * kT + lane, sentinel());
+#pragma unroll 8
+      for (int r = 0; r < kT; r++) stcg(p.Linv + ((size_t)j * kT + r) * kT + lane, sentinel());
+    }
+  } else if (has_tile) {
+    const int c0 = j * kT + lane;
+    if (c0 < n) {
+      if (world > 1) {
+        for (int q = 0; q < world; q++) {
+          double v;
+          asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p.peers.sys[q] + nn + c0) : "memory");
+          y += v;
+        }
+      } else y = p.b[c0];
+    }
+    stcg(yrow + c0, sentinel());
+  }
+  __threadfence();
+  cluster.sync();
+  if (p.timing && cta == 0 && tid == 0) p.timing[0] = p.timing[1] = p.timing[2] = gtimer();
+
+  if (has_tile) {
+    double (*sA)[kTP] = s_A[warp];
+    double (*sB)[kTP] = s_B[warp];
+    bool alive = true;
+
+    if (i < nt) {
+      // ---------------- matrix tile (i, j): updates with the finished columns k < j
+      for (int k = 0; k < j && alive; k++) {
+        const bool last = (i == j && k == j - 1);
+        if (last) RES_STAMP(j, 8);
+        if (last && (p.warm & 2)) {
+          // mode 2: the diagonal owner does not wait for tile (j, j-1) to come back from its owner; it takes that tile as it was BEFORE
+          // the substitution (published early, off the critical path), substitutes against L_{j-1,j-1} itself and updates: one hand-over
+          // per column instead of two.  The owner of (j, j-1) does the same substitution for everybody else.
+          alive = tile_fetch(p.Cs + (size_t)(j - 1) * kT * kT, kT, lane, sA, p.sleep_urgent, p.sleep_urgent);
+          alive = tile_fetch(L + (size_t)((j - 1) * kT) * ld + (j - 1) * kT, ld, lane, sB, p.sleep_urgent, p.sleep_urgent) && alive;
+          double rdl;
+          alive = vec_fetch(p.rdiag + (j - 1) * kT, lane, rdl, p.sleep_urgent) && alive;
+          s_rd[warp][lane] = rdl;
+          __syncwarp();
+          RES_STAMP(j, 9);
+          double x[kT];
+#pragma unroll
+          for (int c = 0; c < kT; c++) x[c] = sA[lane][c];
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < kT; c++) {
+            const double xv = x[c] * s_rd[warp][c];
+            x[c] = xv;
+#pragma unroll
+            for (int jj = c + 1; jj < kT; jj++) x[jj] -= xv * sB[jj][c];
+            asm volatile("" ::: "memory");
+          }
+#pragma unroll
+          for (int c = 0; c < kT; c++) sA[lane][c] = x[c];
+          __syncwarp();
+          slab_mac(acc, sA, sA, lane);
+          RES_STAMP(j, 10);
+          __syncwarp();
+          continue;
+        }
+        const bool urgent = (i <= j + 1) && (k >= j - 2);     // the tile is (about to be) on the critical path
+        const unsigned slp = urgent ? p.sleep_urgent : p.sleep_idle;
+        alive = tile_fetch(L + (size_t)(i * kT) * ld + k * kT, ld, lane, sA, slp, p.sleep_urgent);
+        if (i != j) {
+          alive = tile_fetch(L + (size_t)(j * kT) * ld + k * kT, ld, lane, sB, slp, p.sleep_urgent) && alive;
+          slab_mac(acc, sA, sB, lane);
+        } else {
+          if (last) RES_STAMP(j, 9);
+          slab_mac(acc, sA, sA, lane);
+          if (last) RES_STAMP(j, 10);
+        }
+        __syncwarp();
+      }
+      // ---------------- finalise
+      double* tile = L + (size_t)(i * kT) * ld + j * kT;
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int jx = 0; jx < 4; jx++) sA[8 * rg + a][4 * cgp + jx] = acc[a][jx];
+      __syncwarp();
+      double a[kT];
+#pragma unroll
+      for (int c = 0; c < kT; c++) a[c] = sA[lane][c];                 // lane = row
+      __syncwarp();
+      if (i == j) {
+        RES_STAMP(j, 0);
+        const long long ck0 = clock64();
+        double rd;
+        if (!warp_potrf(a, lane, s_colb[warp], rd) && lane == 0) *p.fail = 1;
+        __syncwarp();
+        RES_STAMP(j, 7);
+        if (p.timing && lane == 0) p.timing[8 + 16 * j + 13] = (unsigned long long)(clock64() - ck0);
+#pragma unroll
+        for (int c = 0; c < kT; c++) sA[lane][c] = (c <= lane) ? a[c] : 0.0;
+        s_rd[warp][lane] = rd;
+        __syncwarp();
+        stcg(p.rdiag + j * kT + lane, rd);
+#pragma unroll 8
+        for (int r = 0; r < kT; r++) stcg(tile + (size_t)r * ld + lane, sA[r][lane]);
+        RES_STAMP(j, 1);
+        // inverse of L_jj for the backward pass (off the critical path): lane c owns column c
+        double xcol[kT];
+#pragma unroll
+        for (int r = 0; r < kT; r++) {
+          double s = 0.0;
+#pragma unroll
+          for (int m = 0; m < r; m++) s += (m >= lane) ? sA[r][m] * xcol[m] : 0.0;
+          xcol[r] = (r == lane) ? s_rd[warp][r] : ((r > lane) ? -s * s_rd[warp][r] : 0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < kT; r++) stcg(p.Linv + ((size_t)j * kT + r) * kT + lane, xcol[r]);
+      } else {
+        const bool sub = (i == j + 1);
+        if (sub && (p.warm & 2)) {
+#pragma unroll 8
+          for (int r = 0; r < kT; r++) stcg(p.Cs + ((size_t)j * kT + r) * kT + lane, sA[r][lane]);
+        }
+        if (sub) RES_STAMP(j, 2);
+        double rdl;
+        const unsigned slp = sub ? p.sleep_urgent : p.sleep_idle;
+        alive = tile_fetch(L + (size_t)(j * kT) * ld + j * kT, ld, lane, sB, slp, p.sleep_urgent) && alive;
+        alive = vec_fetch(p.rdiag + j * kT, lane, rdl, p.sleep_urgent) && alive;
+        s_rd[warp][lane] = rdl;
+        __syncwarp();
+        if (sub) RES_STAMP(j, 4);
+#pragma unroll
+        for (int c = 0; c < kT; c++) {
+          const double xv = a[c] * s_rd[warp][c];
+          a[c] = xv;
+#pragma unroll
+          for (int jj = c + 1; jj < kT; jj++) a[jj] -= xv * sB[jj][c];
+          asm volatile("" ::: "memory");
+        }
+        if (sub) RES_STAMP(j, 5);
+#pragma unroll
+        for (int c = 0; c < kT; c++) sA[lane][c] = a[c];
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < kT; r++) stcg(tile + (size_t)r * ld + lane, sA[r][lane]);
+        if (sub) RES_STAMP(j, 3);
+      }
+    } else {
+      // ---------------- right-hand side piece j: lane c holds entry 32 j + c;  y_j = L_jj^-1 (b_j - sum_k L_jk y_k)
+      for (int k = 0; k < j && alive; k++) {
+        double yk;
+        alive = vec_fetch(yrow + k * kT, lane, yk, p.sleep_idle);
+        alive = tile_fetch(L + (size_t)(j * kT) * ld + k * kT, ld, lane, sA, p.sleep_idle, p.sleep_urgent) && alive;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < kT; c += 2) {
+          s0 += sA[lane][c] * __shfl_sync(0xffffffffu, yk, c);
+          s1 += sA[lane][c + 1] * __shfl_sync(0xffffffffu, yk, c + 1);
+        }
+        y -= s0 + s1;
+        __syncwarp();
+      }
+      double rdl;
+      alive = tile_fetch(L + (size_t)(j * kT) * ld + j * kT, ld, lane, sB, j == nt - 1 ? p.sleep_urgent : p.sleep_idle, p.sleep_urgent) && alive;
+      alive = vec_fetch(p.rdiag + j * kT, lane, rdl, p.sleep_urgent) && alive;
+#pragma unroll
+      for (int c = 0; c < kT; c++) {
+        const double yc = __shfl_sync(0xffffffffu, y, c) * __shfl_sync(0xffffffffu, rdl, c);
+        if (lane == c) y = yc;
+        else if (lane > c) y -= sB[lane][c] * yc;
+      }
+      stcg(yrow + j * kT + lane, y);
+      RES_STAMP(j, 11);
+    }
+    if (!alive && lane == 0) *p.fail = 4;                    // a producer never arrived: give up loudly, never hang
+  }
+  if (cta != 0) return;
+  // ---- backward substitution  L^T x = y  in CTA 0.  No barrier with the other CTAs: every load below validates itself against the
+  //      sentinel (the last things to appear are y_{nt-1} and the inverse of the last diagonal tile).  y lives in shared memory, the
+  //      operands of step k-1 (inverse diagonal tile for warp 0, up to two tiles (k-1, i) per warp) are fetched during step k.
+  __shared__ double s_y[kResMaxNt * kT];
+  auto ld_valid = [&](const double* q) -> double {
+    double v = __ldcg(q);
+    for (int tries = 0; is_sentinel(v) && tries < (1 << 20); tries++) { __nanosleep(100); v = __ldcg(q); }
+    return v;
+  };
+  {                                                          // the last piece of y is the last thing the forward pass produces
+    const double* ylast = yrow + (nt - 1) * kT;
+    for (int tries = 0; tries < (1 << 20); tries++) {
+      const double v = __ldcg(ylast + lane);
+      if (!__any_sync(0xffffffffu, is_sentinel(v))) break;
+      __nanosleep(250);
+    }
+  }
+  for (int q = tid; q < nt * kT; q += kCholThreads) s_y[q] = ld_valid(yrow + q);
+  // warp 0 turns y_k into x_k (inverse diagonal tile prefetched one step ahead); warps 1..7 subtract L_ki^T x_k from the y_i above it,
+  // their tiles (k, i) -- at most two per warp -- fetched into registers before x_k exists.  Named barrier 1: "x_k is in s_vec",
+  // named barrier 2: "step k is folded into s_y".
+  if (warp == 0) {
+    double inv_c[kT], inv_n[kT];
+#pragma unroll
+    for (int r = 0; r < kT; r++) inv_c[r] = __ldcg(p.Linv + ((size_t)(nt - 1) * kT + r) * kT + lane);
+    __syncthreads();
+    if (p.timing && tid == 0) p.timing[4] = gtimer();
+    for (int k = nt - 1; k >= 0; k--) {
+      const double* invp = p.Linv + (size_t)k * kT * kT + lane;
+      if (k > 0) {
+#pragma unroll
+        for (int r = 0; r < kT; r++) inv_n[r] = __ldcg(invp - kT * kT + r * kT);
+      }
+      // x_k = Linv_kk^T y_k : lane c computes sum_r Linv[r][c] * y[r].  A sentinel (a NaN) in an operand shows in the result: only then are
+      // the operands re-read until they are all there -- no per-element test on the fast path
+      const double yk = s_y[k * kT + lane];
+      double xk;
+      for (int tries = 0;; tries++) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+        for (int r = 0; r < kT; r += 4) {
+          s0 += inv_c[r] * __shfl_sync(0xffffffffu, yk, r);
+          s1 += inv_c[r + 1] * __shfl_sync(0xffffffffu, yk, r + 1);
+          s2 += inv_c[r + 2] * __shfl_sync(0xffffffffu, yk, r + 2);
+          s3 += inv_c[r + 3] * __shfl_sync(0xffffffffu, yk, r + 3);
+        }
+        xk = (s0 + s1) + (s2 + s3);
+        if (!__any_sync(0xffffffffu, xk != xk)) break;
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < kT; r++) bad |= is_sentinel(inv_c[r]);
+        if (!__any_sync(0xffffffffu, bad) || tries > (1 << 18)) break;     // a genuine NaN (failed factorisation), or time-out
+        __nanosleep(100);
+#pragma unroll
+        for (int r = 0; r < kT; r++) inv_c[r] = __ldcg(invp + r * kT);
+      }
+      s_vec[lane] = xk;
+      s_y[k * kT + lane] = xk;
+      asm volatile("bar.sync 1, %0;" ::"n"(kCholThreads) : "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(kCholThreads) : "memory");
+      RES_STAMP(k, 12);
+#pragma unroll
+      for (int r = 0; r < kT; r++) inv_c[r] = inv_n[r];
+    }
+  } else {
+    double tl[2][kT];
+    auto fetch_tile = [&](int k, int sl) {
+      const int ii = (warp - 1) + (kCholWarps - 1) * sl;
+      if (ii < k) {
+        const double* tp = L + (size_t)(k * kT) * ld + ii * kT + lane;
+#pragma unroll
+        for (int r = 0; r < kT; r++) tl[sl][r] = __ldcg(tp + (size_t)r * ld);
+      }
+    };
+    __syncthreads();
+    fetch_tile(nt - 1, 0);
+    fetch_tile(nt - 1, 1);
+    for (int k = nt - 1; k >= 0; k--) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kCholThreads) : "memory");
+      // y_i -= L_ki^T x_k : lane = column of tile (k,i)
+#pragma unroll
+      for (int sl = 0; sl < 2; sl++) {
+        const int ii = (warp - 1) + (kCholWarps - 1) * sl;
+        if (ii < k) {
+          double sum;
+          for (int tries = 0;; tries++) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < kT; r += 2) { s0 += tl[sl][r] * s_vec[r]; s1 += tl[sl][r + 1] * s_vec[r + 1]; }
+            sum = s0 + s1;
+            if (!__any_sync(0xffffffffu, sum != sum)) break;
+            bool bad = false;
+#pragma unroll
+            for (int r = 0; r < kT; r++) bad |= is_sentinel(tl[sl][r]);
+            if (!__any_sync(0xffffffffu, bad) || tries > (1 << 18)) break;
+            __nanosleep(100);
+            fetch_tile(k, sl);
+          }
+          s_y[ii * kT + lane] -= sum;
+        }
+      }
+      if (k > 0) { fetch_tile(k - 1, 0); fetch_tile(k - 1, 1); }
+      asm volatile("bar.sync 2, %0;" ::"n"(kCholThreads) : "memory");
+    }
+  }
+  __syncthreads();
+  if (p.timing && tid == 0) p.timing[3] = gtimer();
+  const bool failed = (*reinterpret_cast<volatile int*>(p.fail)) != 0;
+  for (int q = tid; q < n; q += kCholThreads) {
+    const double v = s_y[q];
+    p.x[q] = (failed || !isfinite(v)) ? 0.f : (float)v;      // a failed factorisation leaves NaNs (or sentinels) everywhere: zeros, like the reference
+  }
+}
+
 size_t chol_workspace_bytes(int n) {
   const size_t nt = (size_t)(n + kT - 1) / kT;
   const size_t ld = nt * kT;
-  return ((nt + 1) * kT * ld + nt * kT * kT + nt * kT) * sizeof(double) + (nt + 2) * sizeof(int) + 256;
+  return ((nt + 1) * kT * ld + nt * kT * kT + nt * kT) * sizeof(double) + (nt + 2) * sizeof(int) + 256 +
+         (size_t)(kResMaxNt + 1) * kResMaxNt * sizeof(int) + (size_t)kResMaxNt * kT * kT * sizeof(double) + 256;
 }
 
 // H [n][n] fp64, b [n] fp64 -> x [n] fp32; fail flag is a device int
@@ -437,12 +924,16 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   p.Linv = p.L + (size_t)(p.nt + 1) * kT * ld;
   p.rdiag = p.Linv + (size_t)p.nt * kT * kT;
   p.first = reinterpret_cast<int*>(p.rdiag + (size_t)p.nt * kT);
+  p.flags = p.first + (p.nt + 2);
+  p.Cs = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(p.flags + (kResMaxNt + 1) * kResMaxNt) + 255) & ~(uintptr_t)255);
 
   const size_t dyn_smem = ((size_t)2 * kCholWarps + 2) * kT * kTP * sizeof(double);
   static int cluster_size = 0;
   if (cluster_size == 0) {
     cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    cudaFuncSetAttribute(chol_resident_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(chol_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int best = 8;
     for (int cs = 16; cs >= 8; cs -= 8) {
       cudaLaunchConfig_t cfg = {};
@@ -471,7 +962,39 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   if (want_timing) {
     if (!tbuf) cudaMallocHost(&tbuf, 4096 * sizeof(unsigned long long));
     memset(tbuf, 0, 4096 * sizeof(unsigned long long));
-    if (8 + 8 * p.nt < 4096) p.timing = tbuf;
+    if (8 + 16 * p.nt < 4096) p.timing = tbuf;
+  }
+  // resident-tile dataflow kernel: every tile needs its own warp
+  static const bool allow_resident = !(getenv("DBA_CHOL_RESIDENT") && atoi(getenv("DBA_CHOL_RESIDENT")) == 0);
+  const int res_tiles = p.nt * (p.nt + 1) / 2 + p.nt;
+  const int res_chain_ctas = (2 * p.nt - 1 + kCholWarps - 1) / kCholWarps;     // CTAs reserved for the diagonal / sub-diagonal tiles
+  const int res_ctas = res_chain_ctas + (res_tiles - (2 * p.nt - 1) + kCholWarps - 1) / kCholWarps;
+  if (allow_resident && p.nt <= kResMaxNt && res_ctas <= cluster_size) {
+    int rcs = 1;
+    while (rcs < res_ctas) rcs *= 2;
+    cfg.gridDim = dim3(rcs);
+    at[0].val.clusterDim.x = rcs;
+    static const unsigned sl_u = getenv("DBA_CHOL_SLEEP_URGENT") ? (unsigned)atoi(getenv("DBA_CHOL_SLEEP_URGENT")) : 300u;
+    static const unsigned sl_i = getenv("DBA_CHOL_SLEEP_IDLE") ? (unsigned)atoi(getenv("DBA_CHOL_SLEEP_IDLE")) : 4000u;
+    p.sleep_urgent = sl_u; p.sleep_idle = sl_i;
+    static const int warm = getenv("DBA_CHOL_FUSED_SUBST") ? (atoi(getenv("DBA_CHOL_FUSED_SUBST")) ? 2 : 0) : 2;
+    p.warm = warm;
+    DBA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_resident_kernel, p), "chol_resident_kernel launch");
+    if (p.timing) {
+      cudaStreamSynchronize(st);
+      const unsigned long long t0 = tbuf[0];
+      fprintf(stderr, "[chol resident timing] n=%d nt=%d cluster=%d  factor+forward %.1f us, backsub %.1f us\n", n, p.nt, rcs, (tbuf[4] - t0) / 1e3,
+              (tbuf[3] - tbuf[4]) / 1e3);
+      for (int k = 0; k < p.nt; k++) {
+        const unsigned long long* q = tbuf + 8 + 16 * k;
+        auto d = [&](int a, int b) { return (q[a] && q[b]) ? (double)((long long)q[a] - (long long)q[b]) / 1e3 : 0.0; };
+        fprintf(stderr, "  column %2d: diag: last update starts@%.1f wait+load %.1f mac %.1f transpose %.1f potrf %.1f store %.1f | (k+1,k): ready %+.1f after that, wait+load L_kk %.1f subst %.1f store %.1f\n",
+                k, q[8] ? (q[8] - t0) / 1e3 : 0.0, d(9, 8), d(10, 9), d(0, 10), d(7, 0), d(1, 7), d(2, 1), d(4, 2), d(5, 4), d(3, 5));
+        fprintf(stderr, "             y piece stored@%.1f   backward step done@%.1f   potrf: %llu SM cycles in %.2f us = %.0f MHz\n", q[11] ? (q[11] - t0) / 1e3 : 0.0,
+                q[12] ? (q[12] - t0) / 1e3 : 0.0, q[13], d(7, 0), d(7, 0) > 0 ? (double)q[13] / d(7, 0) : 0.0);
+      }
+    }
+    return DBA_OK;
   }
   DBA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_cluster_kernel, p), "chol_cluster_kernel launch");
   if (p.timing) {

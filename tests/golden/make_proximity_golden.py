@@ -68,6 +68,8 @@ def cases():
 
 
 def import_reference_factor_graph():
+    before = set(sys.modules)
+    path_before = list(sys.path)
     sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
     sys.path.insert(0, os.path.join(REF, "droid_slam"))
     added = []
@@ -83,8 +85,13 @@ def import_reference_factor_graph():
     try:
         fg = importlib.import_module("factor_graph")
     finally:
+        # leave no trace: the reference modules imported here were bound to the empty stubs and must not be found by later importers
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in ("factor_graph", "geom", "modules", "cuda_timer", "matplotlib", "droid_backends"):
+                sys.modules.pop(name, None)
         for name in added:
             sys.modules.pop(name, None)
+        sys.path[:] = path_before
     return fg
 
 

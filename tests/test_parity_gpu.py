@@ -256,7 +256,7 @@ def test_ba_cholesky_failure_gives_zero_update(capi):
 
 
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [6, 30, 42, 100, 426, 1000, 2394])
+@pytest.mark.parametrize("n", [6, 30, 42, 100, 200, 426, 448, 449, 1000, 2394])
 def test_cluster_cholesky_solver_matches_fp64_lapack(capi, n):
     """the standalone damped SPD solve (thread-block-cluster tiled Cholesky, fp64) against torch.linalg in fp64"""
     g = torch.Generator().manual_seed(n)
