@@ -97,6 +97,7 @@ struct CholParams {
   unsigned sleep_urgent, sleep_idle;   // resident-tile kernel: ns between polls of a warp on / off the critical path
   int warm;                            // bit 1: the diagonal owner substitutes tile (j, j-1) itself (default; DBA_CHOL_FUSED_SUBST=0 turns it off)
   double* Cs;                          // resident-tile kernel: [nt][32][32] tiles (j+1, j) BEFORE the substitution (for mode 2)
+  unsigned char map_i[128], map_j[128];   // resident-tile kernel: tile (i, j) of warp slot cta*8 + warp; 0xFF = none
   int* fail;         // sticky flag: non-positive pivot
   float* x;          // [n] result (fp32 like the reference's dx)
   int n, nt;
@@ -138,6 +139,28 @@ __device__ __forceinline__ void warp_tile_update(const double* At, const double*
     __stcg(reinterpret_cast<double2*>(Ct + (size_t)(8 * rg + i) * ld + 4 * cgp + 2), make_double2(acc[i][2], acc[i][3]));
   }
   __syncwarp();
+}
+
+// Cluster-wide barrier WITHOUT the acquire side of barrier.cluster.wait.  Measured on B200 (this kernel, %globaltimer): every acquire --
+// barrier.cluster.wait, ld.acquire, fence -- ends in CCTL.IVALL, and the first global loads a warp issues after it take ~3 us instead of
+// ~0.3.  All data exchanged through this barrier is written with st.global.cg and read with ld.global.cg (L2 on both sides), so no L1
+// line ever has to be invalidated: every thread drains its own stores to L2 with a release store (MEMBAR.ALL.GPU, no CCTL), the CTA
+// meets at bar.sync, ncta of its threads arrive (relaxed) on the ncta per-CTA mbarriers through distributed shared memory, and everyone
+// waits (relaxed) on the local one.
+__device__ __forceinline__ void cluster_sync_light(unsigned mbar, unsigned& phase, int ncta, int tid, unsigned* drain) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(drain), "r"(0u) : "memory");
+  __syncthreads();
+  if (tid < ncta) {
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mbar), "r"((unsigned)tid));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                 : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+  }
+  phase ^= 1u;
 }
 
 __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParams p) {
@@ -187,6 +210,14 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
   // ---- envelope: first[i] starts at the diagonal, the load below lowers it to the first nonzero tile of the row
   const bool envelope = nt < kCholThreads;             // one thread per tile row in the per-panel scan below
   for (int i = cta * kCholThreads + tid; i <= nt; i += ncta * kCholThreads) p.first[i] = (i < nt && envelope) ? i : 0;
+  __shared__ unsigned long long s_mbar;
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar);
+  unsigned mphase = 0;
+  unsigned* drain = reinterpret_cast<unsigned*>(p.first + nt + 1);   // spare word: target of the store-draining release stores
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"((unsigned)ncta) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   cluster.sync();
   // ---- load: lower tiles of H with damping (reference :1205-1206), identity padding, rhs row ------------------
   {
@@ -258,7 +289,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
     for (int c = 0; c < kT; c++) stcg(L + (size_t)lane * ld + c, (c <= lane) ? a[c] : 0.0);
     stcg(p.rdiag + lane, rd);
   }
-  cluster.sync();
+  cluster_sync_light(mbar, mphase, ncta, tid, drain);
   CHOL_STAMP(2);
 
   for (int k = 0; k < nt; k++) {
@@ -310,7 +341,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
       __syncwarp();
     }
     CHOL_STAMP(8 + 8 * k + 1);
-    cluster.sync();
+    cluster_sync_light(mbar, mphase, ncta, tid, drain);
     CHOL_STAMP(8 + 8 * k + 2);
     // ---- trailing update with panel k
     const int rem = nt - k - 1;                       // remaining tile columns
@@ -389,7 +420,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
 #pragma unroll
       for (int i = 0; i < kT; i++) stcg(p.Linv + ((size_t)k * kT + i) * kT + lane, xcol[i]);
     }
-    cluster.sync();
+    cluster_sync_light(mbar, mphase, ncta, tid, drain);
     CHOL_STAMP(8 + 8 * k + 4);
   }
 
@@ -554,32 +585,10 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholPara
     if (cta == 0 && tid == 0) *p.fail = s_timeout ? 2 : 0;
   } else if (cta == 0 && tid == 0) *p.fail = 0;
 
-  // ---- tile of this warp.  The critical path runs through the diagonal tiles and the tiles right below them; they get CTAs of their own
-  //      (measured: a potrf takes 5.4 us next to seven warps doing trailing updates and 2.9 us on a quiet SM, a substitution 2.2 vs 1.0),
-  //      diagonal tiles first so that the potrf code stays in those SMs' instruction caches.  Every other tile and the right-hand side
-  //      pieces are dealt round-robin (column-major, so one column's tiles -- which become ready together -- sit on different SMs).
-  const int ntiles = nt * (nt + 1) / 2 + nt;
-  const int nchain = 2 * nt - 1;
-  const int chain_ctas = (nchain + kCholWarps - 1) / kCholWarps;
-  bool has_tile = false;
-  int i = 0, j = 0;
-  if (cta < chain_ctas) {
-    const int slot = cta * kCholWarps + warp;
-    if (slot < nt) { has_tile = true; i = j = slot; }
-    else if (slot < nchain) { has_tile = true; j = slot - nt; i = j + 1; }
-  } else {
-    int rem = (cta - chain_ctas) + (ncta - chain_ctas) * warp;       // index into the other tiles, column-major
-    if (rem < ntiles - nchain) {
-      has_tile = true;
-      while (true) {
-        const int cnt = (nt - 2 - j > 0 ? nt - 2 - j : 0) + 1;       // tiles (j+2 .. nt-1, j) and the right-hand side piece (nt, j)
-        if (rem < cnt) break;
-        rem -= cnt; j++;
-      }
-      const int below = (nt - 2 - j > 0 ? nt - 2 - j : 0);
-      i = (rem < below) ? j + 2 + rem : nt;
-    }
-  }
+  // ---- tile of this warp: placed by the host (resident_tile_map below) so that a potrf never shares its SM with a working warp
+  const int slot = cta * kCholWarps + warp;
+  const bool has_tile = p.map_i[slot] != 0xFF;
+  const int i = has_tile ? (int)p.map_i[slot] : 0, j = has_tile ? (int)p.map_j[slot] : 0;
   const int rg = lane >> 3, cgp = lane & 7;
   double acc[8][4];
   double y = 0.0;
@@ -905,6 +914,43 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholPara
   }
 }
 
+// Placement of the resident kernel's tiles on the cluster's warp slots.  The fp64 pipe of an SM is narrow (64 lanes/clk, measured) and the
+// potrf of a diagonal tile is a chain of ~8 dependent fp64 operations per column: measured, it takes 5.3 us while other warps of the
+// SM stream the DFMAs of their trailing updates and 2.9 us alone.  A tile of column c works until column c is finished, and potrf(s)
+// runs when column s-1 is finished, so diagonal tile s gets CTA s to itself *in time*: a column-c tile may only share that SM if c < s
+// (finished before), if the SM has no diagonal tile (s >= nt), or if s == 0 (potrf(0) runs before anything else has operands).
+// Tiles of one column substitute at the same time and are spread over different SMs where possible.  Returns false if ncta is too small.
+static bool resident_tile_map(int nt, int ncta, unsigned char* map_i, unsigned char* map_j) {
+  int nfree[16], used[16][kCholWarps];
+  unsigned colmask[16];
+  for (int s = 0; s < 16; s++) { nfree[s] = kCholWarps; colmask[s] = 0; for (int w = 0; w < kCholWarps; w++) used[s][w] = 0; }
+  for (int q = 0; q < 128; q++) map_i[q] = map_j[q] = 0xFF;
+  if (ncta > 16 || ncta < nt) return false;
+  auto place = [&](int s, int i, int j) {
+    for (int w = 0; w < kCholWarps; w++)
+      if (!used[s][w]) { used[s][w] = 1; nfree[s]--; map_i[s * kCholWarps + w] = (unsigned char)i; map_j[s * kCholWarps + w] = (unsigned char)j; return; }
+  };
+  for (int j = 0; j < nt; j++) place(j, j, j);
+  for (int c = nt - 1; c >= 0; c--) {
+    for (int i = c + 1; i <= nt; i++) {                      // i == nt: the right-hand side piece of column c
+      int best = -1, best_key = 1 << 30;
+      for (int pass = 0; pass < 2 && best < 0; pass++) {
+        for (int s = 0; s < ncta; s++) {
+          if (nfree[s] == 0) continue;
+          const bool eligible = (s > c) || (s >= nt) || (s == 0);
+          if (pass == 0 && !eligible) continue;
+          const int key = (((colmask[s] >> c) & 1u) ? 4096 : 0) + ((s > c && s < nt) ? 0 : 1024) + (kCholWarps - nfree[s]) * 16 + s;
+          if (key < best_key) { best_key = key; best = s; }
+        }
+      }
+      if (best < 0) return false;
+      place(best, i, c);
+      colmask[best] |= 1u << c;
+    }
+  }
+  return true;
+}
+
 size_t chol_workspace_bytes(int n) {
   const size_t nt = (size_t)(n + kT - 1) / kT;
   const size_t ld = nt * kT;
@@ -967,11 +1013,9 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   // resident-tile dataflow kernel: every tile needs its own warp
   static const bool allow_resident = !(getenv("DBA_CHOL_RESIDENT") && atoi(getenv("DBA_CHOL_RESIDENT")) == 0);
   const int res_tiles = p.nt * (p.nt + 1) / 2 + p.nt;
-  const int res_chain_ctas = (2 * p.nt - 1 + kCholWarps - 1) / kCholWarps;     // CTAs reserved for the diagonal / sub-diagonal tiles
-  const int res_ctas = res_chain_ctas + (res_tiles - (2 * p.nt - 1) + kCholWarps - 1) / kCholWarps;
-  if (allow_resident && p.nt <= kResMaxNt && res_ctas <= cluster_size) {
-    int rcs = 1;
-    while (rcs < res_ctas) rcs *= 2;
+  int rcs = 1;
+  while (rcs * kCholWarps < res_tiles || rcs < p.nt) rcs *= 2;
+  if (allow_resident && p.nt <= kResMaxNt && rcs <= cluster_size && resident_tile_map(p.nt, rcs, p.map_i, p.map_j)) {
     cfg.gridDim = dim3(rcs);
     at[0].val.clusterDim.x = rcs;
     static const unsigned sl_u = getenv("DBA_CHOL_SLEEP_URGENT") ? (unsigned)atoi(getenv("DBA_CHOL_SLEEP_URGENT")) : 300u;
