@@ -603,9 +603,10 @@ def secondary_kernels(E, dev, ms_step, L, be):
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         ms = _time_ms(lambda: L.dba_solve_spd(vp(H), vp(bvec), n, ctypes.c_float(1e-4), ctypes.c_float(0.1), vp(x), vp(fail), vp(ws), ctypes.c_size_t(wsb), st), iters=20)
         fl = n ** 3 / 3.0
-        out["rooflines"].append({"kernel": "chol_cluster_kernel (n = %d, fp64)" % n, "bound": "fp64 issue rate", "achieved": fl / ms / 1e9, "peak": 34.0, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / 34.0,
+        kname = "chol_resident_kernel" if n <= 448 and os.environ.get("DBA_CHOL_RESIDENT", "1") != "0" else "chol_cluster_kernel"
+        out["rooflines"].append({"kernel": "%s (n = %d, fp64)" % (kname, n), "bound": "fp64 issue rate", "achieved": fl / ms / 1e9, "peak": 34.0, "unit": "TFLOP/s", "frac": fl / ms / 1e9 / 34.0,
                                  "peak_source": "measured fp64 FMA issue rate (profiles/r1_fp64_issue_rate.txt)", "ms": ms, "algorithmic_flops": fl,
-                                 "note": "latency bound: a chain of n/32 dependent panel steps, the figure of merit is the time"})
+                                 "note": "latency bound: a chain of n/32 dependent column steps (potrf -> substitution -> update), the figure of merit is the time"})
     except Exception as e:
         out["rooflines"].append({"kernel": "chol_cluster_kernel", "error": str(e)[:200]})
     return out

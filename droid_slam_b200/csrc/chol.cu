@@ -543,8 +543,62 @@ __device__ __forceinline__ size_t sys_index(int r, int c, int n, bool diag_tile)
   return (size_t)-1;
 }
 
+// Cholesky of a 32x32 tile, one row per lane, in ~300 instructions instead of the ~1800 straight-line ones of warp_potrf.  ncu on the
+// resident kernel (profiles/r2_chol_resident_stalls.txt): 40 % of the samples inside the unrolled potrf are "no instruction" -- the code is
+// executed once per SM and its delivery from the GPC-level instruction cache, not its dependent chain, sets the pace (2.9 us on an idle
+// GPC, 5.3 us while the other 15 SMs fetch code of their own).  Here the row is shifted down one register per column, so a[0] is always
+// the pivot column and all register indices are static inside a rolled loop; four loops of eight columns with widths 32/24/16/8 keep
+// the extra arithmetic at 608 instead of 496 DFMAs.  The pivot column is published twice (offset by one double) so that the operands
+// of the rank-1 update can be fetched with aligned 16-byte loads whatever the parity of the column.  Per element the operations and
+// their order are those of warp_potrf: identical bits.  out[lane][k] receives L (zeros above the diagonal).
+template <int W>
+__device__ __forceinline__ void potrf_phase(double (&a)[kT], int lane, int k0, double* cx, double* cy, double (*out)[kTP], double& d, double& r, bool& ok,
+                                            double& rdiag_out) {
+#pragma unroll 1
+  for (int k = k0; k < k0 + 8; k++) {
+    if (!(d > 0.0)) ok = false;
+    const double l = (lane == k) ? d * r : a[0] * r;
+    if (lane == k) rdiag_out = r;
+    out[lane][k] = (lane >= k) ? l : 0.0;
+    double* bx = cx + (k & 1) * (2 * kT + 2);               // double-buffered over k: no second barrier per column
+    double* by = cy + (k & 1) * (2 * kT + 2);
+    bx[lane] = l;                                            // bx[t]     = l of row t
+    by[lane + 1] = l;                                        // by[t + 1] = l of row t
+    __syncwarp();
+    const double* ck = ((k + 1) & 1) ? (by + k + 2) : (bx + k + 1);   // ck[m] = l of row k+1+m, 16-byte aligned either way
+    const double2 c01 = *reinterpret_cast<const double2*>(ck);
+    const double a0 = a[1] - l * c01.x;
+    d = __shfl_sync(0xffffffffu, a0, (k + 1) & 31);
+    r = fast_rsqrt(d);
+    if (W > 2) a[1] = a[2] - l * c01.y;
+#pragma unroll
+    for (int m = 2; m + 1 < W - 1; m += 2) {
+      const double2 c = *reinterpret_cast<const double2*>(ck + m);
+      a[m] = a[m + 1] - l * c.x;
+      a[m + 1] = a[m + 2] - l * c.y;
+    }
+    if (((W - 1) & 1) && W > 3) a[W - 2] = a[W - 1] - l * ck[W - 2];   // odd count: one element left (W - 1 updates in total)
+    a[0] = a0;
+  }
+}
+
+__device__ __forceinline__ bool warp_potrf_compact(double (&a)[kT], int lane, double* cbuf, double (*out)[kTP], double& rdiag_out) {
+  bool ok = true;
+  rdiag_out = 0.0;
+  double* cx = cbuf;                                         // 2 x (2*kT + 2) doubles
+  double* cy = cbuf + 2 * (2 * kT + 2);                      // 2 x (2*kT + 2) doubles; both 16-byte aligned
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  double r = fast_rsqrt(d);
+  potrf_phase<32>(a, lane, 0, cx, cy, out, d, r, ok, rdiag_out);
+  potrf_phase<24>(a, lane, 8, cx, cy, out, d, r, ok, rdiag_out);
+  potrf_phase<16>(a, lane, 16, cx, cy, out, d, r, ok, rdiag_out);
+  potrf_phase<8>(a, lane, 24, cx, cy, out, d, r, ok, rdiag_out);
+  return ok;
+}
+
 #define RES_STAMP(col, slot) do { if (p.timing && lane == 0) p.timing[8 + 16 * (col) + (slot)] = gtimer(); } while (0)
 
+template <bool PEERS>
 __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const int ncta = (int)cluster.num_blocks();
@@ -554,11 +608,11 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholPara
   const int ld = nt * kT;
   double* __restrict__ L = p.L;
   double* yrow = L + (size_t)(nt * kT) * ld;
-  const int world = p.peers.world;
+  const int world = PEERS ? p.peers.world : 0;
   const size_t nn = (size_t)n * n;
 
   __shared__ double s_rd[kCholWarps][kT];
-  __shared__ double s_colb[kCholWarps][2 * kT];
+  __shared__ __align__(16) double s_colb[kCholWarps][4 * (2 * kT + 2)];
   __shared__ double s_vec[kT];
   extern __shared__ double s_dyn[];
   double (*s_A)[kT][kTP] = reinterpret_cast<double (*)[kT][kTP]>(s_dyn);
@@ -566,7 +620,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholPara
 
   // ---- prologue: wait for the peers' systems (multi-GPU), dense envelope for the backward pass
   for (int i = cta * kCholThreads + tid; i <= nt; i += ncta * kCholThreads) p.first[i] = 0;
-  if (world > 1) {
+  if (PEERS) {
     __shared__ int s_timeout;
     if (tid == 0) {
       int bad = 0;
@@ -603,7 +657,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholPara
         const size_t src = sys_index(r, c, n, i == j);
         double v = (src == (size_t)-1 && r == c) ? 1.0 : 0.0;
         if (src != (size_t)-1) {
-          if (world > 1) {
+          if (PEERS) {
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               t[q] = 0.0;
@@ -634,7 +688,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholPara
   } else if (has_tile) {
     const int c0 = j * kT + lane;
     if (c0 < n) {
-      if (world > 1) {
+      if (PEERS) {
         for (int q = 0; q < world; q++) {
           double v;
           asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p.peers.sys[q] + nn + c0) : "memory");
@@ -717,29 +771,28 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_resident_kernel(CholPara
         RES_STAMP(j, 0);
         const long long ck0 = clock64();
         double rd;
-        if (!warp_potrf(a, lane, s_colb[warp], rd) && lane == 0) *p.fail = 1;
+        if (!warp_potrf_compact(a, lane, s_colb[warp], sA, rd) && lane == 0) *p.fail = 1;
+        s_rd[warp][lane] = rd;
         __syncwarp();
         RES_STAMP(j, 7);
         if (p.timing && lane == 0) p.timing[8 + 16 * j + 13] = (unsigned long long)(clock64() - ck0);
-#pragma unroll
-        for (int c = 0; c < kT; c++) sA[lane][c] = (c <= lane) ? a[c] : 0.0;
-        s_rd[warp][lane] = rd;
-        __syncwarp();
         stcg(p.rdiag + j * kT + lane, rd);
 #pragma unroll 8
         for (int r = 0; r < kT; r++) stcg(tile + (size_t)r * ld + lane, sA[r][lane]);
         RES_STAMP(j, 1);
-        // inverse of L_jj for the backward pass (off the critical path): lane c owns column c
-        double xcol[kT];
-#pragma unroll
+        // inverse of L_jj for the backward pass (off the critical path), rolled: lane c owns column c of X = L^-1, kept in the warp's
+        // second slab;  X[r][c] = (delta_rc - sum_{m<r} L[r][m] X[m][c]) / L[r][r]  (entries above the diagonal come out as zeros)
+#pragma unroll 1
         for (int r = 0; r < kT; r++) {
-          double s = 0.0;
-#pragma unroll
-          for (int m = 0; m < r; m++) s += (m >= lane) ? sA[r][m] * xcol[m] : 0.0;
-          xcol[r] = (r == lane) ? s_rd[warp][r] : ((r > lane) ? -s * s_rd[warp][r] : 0.0);
+          double s0 = 0.0, s1 = 0.0;
+          int m = 0;
+#pragma unroll 1
+          for (; m + 1 < r; m += 2) { s0 += sA[r][m] * sB[m][lane]; s1 += sA[r][m + 1] * sB[m + 1][lane]; }
+          if (m < r) s0 += sA[r][m] * sB[m][lane];
+          sB[r][lane] = (((r == lane) ? 1.0 : 0.0) - (s0 + s1)) * s_rd[warp][r];
         }
-#pragma unroll
-        for (int r = 0; r < kT; r++) stcg(p.Linv + ((size_t)j * kT + r) * kT + lane, xcol[r]);
+#pragma unroll 4
+        for (int r = 0; r < kT; r++) stcg(p.Linv + ((size_t)j * kT + r) * kT + lane, sB[r][lane]);
       } else {
         const bool sub = (i == j + 1);
         if (sub && (p.warm & 2)) {
@@ -978,8 +1031,10 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
   if (cluster_size == 0) {
     cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
-    cudaFuncSetAttribute(chol_resident_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    cudaFuncSetAttribute(chol_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    cudaFuncSetAttribute(chol_resident_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(chol_resident_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    cudaFuncSetAttribute(chol_resident_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(chol_resident_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int best = 8;
     for (int cs = 16; cs >= 8; cs -= 8) {
       cudaLaunchConfig_t cfg = {};
@@ -1023,7 +1078,8 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
     p.sleep_urgent = sl_u; p.sleep_idle = sl_i;
     static const int warm = getenv("DBA_CHOL_FUSED_SUBST") ? (atoi(getenv("DBA_CHOL_FUSED_SUBST")) ? 2 : 0) : 2;
     p.warm = warm;
-    DBA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_resident_kernel, p), "chol_resident_kernel launch");
+    if (p.peers.world > 1) DBA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_resident_kernel<true>, p), "chol_resident_kernel launch");
+    else DBA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, chol_resident_kernel<false>, p), "chol_resident_kernel launch");
     if (p.timing) {
       cudaStreamSynchronize(st);
       const unsigned long long t0 = tbuf[0];
