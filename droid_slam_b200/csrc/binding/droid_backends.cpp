@@ -386,6 +386,32 @@ torch::Tensor cvx_upsample(torch::Tensor disps, torch::Tensor mask) {
   return out;
 }
 
+// extension (row F1): the edge selection of FactorGraph.add_proximity_factors (reference factor_graph.py:357-411) on the device.
+// d [(t-t0)*(t-t1)] f32 as returned by frame_distance over the meshgrid of :351-356, ii_known / jj_known int64 = the graph's active, bad
+// and inactive edges.  Returns es [n,2] int64 in the reference's emission order (one host read of the row count).
+torch::Tensor proximity_edges(torch::Tensor d, int64_t t0, int64_t t1, int64_t t, torch::Tensor ii_known, torch::Tensor jj_known, int64_t rad, int64_t nms,
+                              double thresh, int64_t max_factors, bool stereo) {
+  CHECK_INPUT(d); CHECK_F32(d); CHECK_INPUT(ii_known); CHECK_INPUT(jj_known);
+  TORCH_CHECK(ii_known.scalar_type() == torch::kInt64 && jj_known.scalar_type() == torch::kInt64 && ii_known.numel() == jj_known.numel(), "ii_known / jj_known: int64, same length");
+  TORCH_CHECK(t0 >= 0 && t1 >= 0, "t0, t1 >= 0");
+  c10::cuda::CUDAGuard guard(d.device());
+  const int64_t n_i = std::max<int64_t>(t - t0, 0), n_j = std::max<int64_t>(t - t1, 0), n = n_i * n_j;
+  TORCH_CHECK(d.numel() == n, "d must hold (t - t0) * (t - t1) distances");
+  const int64_t cap = 2 * n + (3 + 2 * rad) * n_i + 2;
+  auto es = torch::empty({cap, 2}, ii_known.options());
+  auto hdr = torch::zeros({2}, torch::dtype(torch::kInt32).device(d.device()));
+  const size_t wsb = dba_proximity_workspace_bytes((int)t0, (int)t1, (int)t);
+  auto ws = torch::empty({(int64_t)wsb}, torch::dtype(torch::kUInt8).device(d.device()));
+  check_status(dba_proximity_edges(d.data_ptr<float>(), (int)t0, (int)t1, (int)t, ii_known.data_ptr<int64_t>(), jj_known.data_ptr<int64_t>(), (int)ii_known.numel(), (int)rad,
+                                   (int)nms, (float)thresh, (int)max_factors, stereo ? 1 : 0, es.data_ptr<int64_t>(), (int)cap, hdr.data_ptr<int>(), ws.data_ptr(), wsb,
+                                   cur_stream()), "proximity_edges");
+  auto h = hdr.cpu();
+  const int rows = h.data_ptr<int>()[0], status = h.data_ptr<int>()[1];
+  TORCH_CHECK((status & 2) == 0, "proximity_edges: index (i - t0) * (t - t1) + (j - t1) out of range (the reference raises IndexError here)");
+  TORCH_CHECK((status & 1) == 0, "proximity_edges: internal capacity exceeded");
+  return es.narrow(0, 0, rows);
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native droid_backends (drop-in for princeton-vl/DROID-SLAM src/droid.cpp)";
   // bundle adjustment kernels
@@ -408,5 +434,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("update_forward", &update_forward, "update operator (ConvGRU + heads + GraphAgg) on tcgen05, B200 extension");
   m.def("conv_nhwc", &conv_nhwc, "channels-last 1x1/3x3 convolution on tcgen05, B200 extension");
   m.def("cvx_upsample", &cvx_upsample, "convex upsampling of inverse depth maps (droid_net.cvx_upsample, dim = 1), B200 extension");
+  m.def("proximity_edges", &proximity_edges, "edge selection of FactorGraph.add_proximity_factors (factor_graph.py:357-411), B200 extension");
   m.def("_b200_native", []() { return true; });
 }

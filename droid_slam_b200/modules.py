@@ -8,12 +8,14 @@ kernel for is offered as a hook:
     its four pyramid levels with the one-pass tcgen05 kernel `droid_backends.corr_volume_pyramid` instead.  Only the constructor is
     replaced; lookups, `cat` and `__getitem__` stay the reference's code.
   * `reproject(...)`: `DepthVideo.reproject` (depth_video.py:171-179 -> geom/projective_ops.py:165-198) as one kernel.
+  * `add_proximity_factors(graph, ...)` / `install_proximity_hook(FactorGraph)`: the edge selection of
+    `FactorGraph.add_proximity_factors` (factor_graph.py:346-412) on the device (row F1).
 """
 import torch
 
 from . import install
 
-__all__ = ["install_corr_volume_hook", "reproject", "upsample"]
+__all__ = ["install_corr_volume_hook", "reproject", "upsample", "add_proximity_factors", "install_proximity_hook"]
 
 
 def install_corr_volume_hook(corr_module, strict=True, fused_lookup=False):
@@ -66,3 +68,31 @@ def upsample(disps, disps_up, ix, mask):
     m = mask.reshape(-1, 576, disps.shape[1], disps.shape[2]).contiguous()
     disps_up[ix] = be.cvx_upsample(disps[ix].contiguous(), m)
     return disps_up
+
+
+def add_proximity_factors(graph, t0=0, t1=0, rad=2, nms=2, beta=0.25, thresh=16.0, remove=False):
+    """FactorGraph.add_proximity_factors (reference factor_graph.py:346-412) with the edge selection on the device (row F1).
+
+    Same signature and effect as the reference method, `graph` being the reference's FactorGraph instance: the distance matrix stays on the
+    GPU (`video.distance` -> droid_backends.frame_distance), masking / suppression / greedy selection run in
+    `droid_backends.proximity_edges` (csrc/proximity.cu) instead of the Python triple loop over a CPU copy, and the resulting edge list
+    -- identical, order included -- goes to the graph's own `add_factors`.  One host read (the number of edges) instead of the
+    reference's `.cpu()` round trips."""
+    be = install()
+    video = graph.video
+    t = video.counter.value
+    dev = graph.ii.device
+    ix = torch.arange(t0, t, device=dev)
+    jx = torch.arange(t1, t, device=dev)
+    ii, jj = torch.meshgrid(ix, jx, indexing="ij")
+    d = video.distance(ii.reshape(-1), jj.reshape(-1), beta=beta).float().contiguous()
+    ii1 = torch.cat([graph.ii, graph.ii_bad, graph.ii_inac], 0).to(torch.long).contiguous()
+    jj1 = torch.cat([graph.jj, graph.jj_bad, graph.jj_inac], 0).to(torch.long).contiguous()
+    es = be.proximity_edges(d, int(t0), int(t1), int(t), ii1, jj1, int(rad), int(nms), float(thresh), int(graph.max_factors), bool(video.stereo))
+    graph.add_factors(es[:, 0].contiguous(), es[:, 1].contiguous(), remove)
+
+
+def install_proximity_hook(factor_graph_class):
+    """replace `add_proximity_factors` of the reference's FactorGraph class (factor_graph.py:346) by the device version"""
+    factor_graph_class.add_proximity_factors = add_proximity_factors
+    return factor_graph_class

@@ -117,6 +117,21 @@ int dba_iproj(const float* poses, const float* disps, const float* intrinsics, f
  * update operator's `upmask`), out [n,8*ht,8*wd] f32 = softmax-over-taps weighted sum of the 3x3 neighbourhood (zero padded). */
 int dba_cvx_upsample(const float* disps, const void* mask, float* out, int n, int ht, int wd, int mask_dtype, dba_stream_t stream);
 
+/* ---- factor-graph edge selection (row F1) --------------------------------------------------------
+ * replaces the body of FactorGraph.add_proximity_factors between `video.distance(...)` and `add_factors(...)` (reference
+ * droid_slam/factor_graph.py:357-411: masking, suppression around the edges the graph already has, temporal-neighbour edges, then the
+ * greedy selection by increasing distance with non-maximum suppression -- a Python / NumPy triple loop on a CPU copy of d).
+ * d [(t-t0)*(t-t1)] f32: frame distances over the grid i in [t0,t), j in [t1,t), row-major (what dba_frame_distance returns for the
+ * meshgrid of factor_graph.py:351-356), read only.  ii_known / jj_known [n_known] int64: cat(ii, ii_bad, ii_inac) / cat(jj, ...).
+ * es [cap][2] int64 receives the (i, j) rows in the reference's emission order; n_out_status [2] int32 on the device: [0] rows written,
+ * [1] status (bit 0: cap too small, bit 1: the reference's unchecked index d[(i-t0)*(t-t1) + (j-t1)] left the array, where it raises
+ * IndexError).  cap >= 2*n + (1+2*(rad+1))*(t-t0) always suffices.  Equal finite distances are visited in index order (torch.argsort
+ * gives no order for ties).  No host synchronisation. */
+size_t dba_proximity_workspace_bytes(int t0, int t1, int t);
+int dba_proximity_edges(const float* d, int t0, int t1, int t, const int64_t* ii_known, const int64_t* jj_known, int n_known, int rad, int nms,
+                        float thresh, int max_factors, int stereo, int64_t* es, int cap, int* n_out_status, void* workspace, size_t workspace_bytes,
+                        dba_stream_t stream);
+
 /* ---- dense bundle adjustment --------------------------------------------------------------------
  * replaces ba_cuda (reference src/droid_kernels.cu:1323-1443, bound at src/droid.cpp:93-122).
  * In place on poses [n_frames,7] and disps [n_frames,ht,wd]; disps_sens like disps; targets, weights
