@@ -483,7 +483,7 @@ def run_ours(args, rank, world, dev):
                                  "step_ms_with_dropin_lookup": ms_step - corr_ms + dropin_ms, "value_with_dropin_lookup": mult * 1e3 / (ms_step - corr_ms + dropin_ms),
                                  "traffic": (traffic or {}).get("dram_bytes_per_step_" + args.dtype), "outputs": "bit-identical to the fused lookup (checked in this run)"}
     if world == 1 and not args.no_extras:
-        extras = secondary_kernels(E, dev, ms_step, L, be)
+        extras = secondary_kernels(E, dev, ms_step, L, be, cpu_legs=not args.no_cpu_baseline)
         line["update_operator"] = extras.pop("update_operator")
         line["rooflines"] = extras["rooflines"]
     if world == 1 and not args.no_cpu_baseline and CFG_NAME in ("metric", "c2", "c4"):
@@ -503,7 +503,7 @@ def _time_ms(fn, iters=5, warm=2):
     return e0.elapsed_time(e1) / iters
 
 
-def secondary_kernels(E, dev, ms_step, L, be):
+def secondary_kernels(E, dev, ms_step, L, be, cpu_legs=True):
     """The other kernels of the path, each timed on its own with CUDA events (not part of `value`): the update operator (row A6,
     tcgen05 convolutions), the correlation-volume build (A7), altcorr (A2), the streaming geometry ops (A8-A11) and the fp64 solve.
     Each entry carries its algorithmic work and the roofline it is held against.  Failures are reported, never raised."""
@@ -609,6 +609,32 @@ def secondary_kernels(E, dev, ms_step, L, be):
                                  "note": "latency bound: a chain of n/32 dependent column steps (potrf -> substitution -> update), the figure of merit is the time"})
     except Exception as e:
         out["rooflines"].append({"kernel": "chol_cluster_kernel", "error": str(e)[:200]})
+    # ---- row F1: proximity edge selection (frontend window and a global-BA sized grid), with the reference's Python loop restated on the CPU beside it
+    try:
+        import time as _time
+        _prox = None
+        if cpu_legs:                                         # CPU baseline leg (like `cpu_baseline`): the oracle is only ever the thing timed beside / checked against
+            import oracle.proximity as _prox
+        for (t, t0, t1, nms, th, mf, tag) in ((30, 25, 5, 1, 16.0, -1, "frontend window 5 x 25 pairs"), (400, 0, 0, 2, 22.0, -1, "global BA 400 x 400 pairs")):
+            gg = torch.Generator().manual_seed(11)
+            ni, nj = t - t0, t - t1
+            fi = torch.arange(t0, t, dtype=torch.float32)[:, None]; fj = torch.arange(t1, t, dtype=torch.float32)[None, :]
+            dm = (6.0 * (fi - fj).abs() * (0.6 + 0.8 * torch.rand(ni, nj, generator=gg)) + torch.rand(ni, nj, generator=gg)).reshape(-1)
+            dm = torch.where(torch.rand(ni * nj, generator=gg) < 0.08, 2.0 + 12.0 * torch.rand(ni * nj, generator=gg), dm)
+            dd = dm.to(dev)
+            known = torch.zeros(0, dtype=torch.long, device=dev)
+            es = be.proximity_edges(dd, t0, t1, t, known, known, 2, nms, th, mf, False)
+            ms = _time_ms(lambda: be.proximity_edges(dd, t0, t1, t, known, known, 2, nms, th, mf, False), iters=20)
+            entry = {"kernel": "proximity_edges (row F1, %s)" % tag, "bound": "latency (serial greedy selection)", "ms": ms, "edges_selected": int(es.shape[0]),
+                     "note": "ms includes the one host read of the edge count; cpu_restatement_ms = oracle/proximity.py (the reference's Python loop restated), one core"}
+            if _prox is not None:
+                c0 = _time.perf_counter()
+                want, _ = _prox.proximity_edges(dm.numpy(), t0, t1, t, [], [], rad=2, nms=nms, thresh=th, max_factors=mf)
+                entry["cpu_restatement_ms"] = 1e3 * (_time.perf_counter() - c0)
+                entry["identical_to_cpu_restatement"] = bool(es.shape[0] == want.shape[0] and (es.cpu().numpy() == want).all())
+            out["rooflines"].append(entry)
+    except Exception as e:
+        out["rooflines"].append({"kernel": "proximity_edges", "error": str(e)[:200]})
     return out
 
 
