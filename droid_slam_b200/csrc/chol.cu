@@ -86,6 +86,59 @@ __device__ __forceinline__ bool warp_potrf(double (&a)[kT], int lane, double* co
   return ok;
 }
 
+// Cholesky of a 32x32 tile, one row per lane, in ~300 instructions instead of the ~1800 straight-line ones of warp_potrf.  ncu on the
+// resident kernel (profiles/r2_chol_resident_stalls.txt): 40 % of the samples inside the unrolled potrf are "no instruction" -- the code is
+// executed once per SM and its delivery from the GPC-level instruction cache, not its dependent chain, sets the pace (2.9 us on an idle
+// GPC, 5.3 us while the other 15 SMs fetch code of their own).  Here the row is shifted down one register per column, so a[0] is always
+// the pivot column and all register indices are static inside a rolled loop; four loops of eight columns with widths 32/24/16/8 keep
+// the extra arithmetic at 608 instead of 496 DFMAs.  The pivot column is published twice (offset by one double) so that the operands
+// of the rank-1 update can be fetched with aligned 16-byte loads whatever the parity of the column.  Per element the operations and
+// their order are those of warp_potrf: identical bits.  out[lane][k] receives L (zeros above the diagonal).
+template <int W>
+__device__ __forceinline__ void potrf_phase(double (&a)[kT], int lane, int k0, double* cx, double* cy, double (*out)[kTP], double& d, double& r, bool& ok,
+                                            double& rdiag_out) {
+#pragma unroll 1
+  for (int k = k0; k < k0 + 8; k++) {
+    if (!(d > 0.0)) ok = false;
+    const double l = (lane == k) ? d * r : a[0] * r;
+    if (lane == k) rdiag_out = r;
+    out[lane][k] = (lane >= k) ? l : 0.0;
+    double* bx = cx + (k & 1) * (2 * kT + 2);               // double-buffered over k: no second barrier per column
+    double* by = cy + (k & 1) * (2 * kT + 2);
+    bx[lane] = l;                                            // bx[t]     = l of row t
+    by[lane + 1] = l;                                        // by[t + 1] = l of row t
+    __syncwarp();
+    const double* ck = ((k + 1) & 1) ? (by + k + 2) : (bx + k + 1);   // ck[m] = l of row k+1+m, 16-byte aligned either way
+    const double2 c01 = *reinterpret_cast<const double2*>(ck);
+    const double a0 = a[1] - l * c01.x;
+    d = __shfl_sync(0xffffffffu, a0, (k + 1) & 31);
+    r = fast_rsqrt(d);
+    if (W > 2) a[1] = a[2] - l * c01.y;
+#pragma unroll
+    for (int m = 2; m + 1 < W - 1; m += 2) {
+      const double2 c = *reinterpret_cast<const double2*>(ck + m);
+      a[m] = a[m + 1] - l * c.x;
+      a[m + 1] = a[m + 2] - l * c.y;
+    }
+    if (((W - 1) & 1) && W > 3) a[W - 2] = a[W - 1] - l * ck[W - 2];   // odd count: one element left (W - 1 updates in total)
+    a[0] = a0;
+  }
+}
+
+__device__ __forceinline__ bool warp_potrf_compact(double (&a)[kT], int lane, double* cbuf, double (*out)[kTP], double& rdiag_out) {
+  bool ok = true;
+  rdiag_out = 0.0;
+  double* cx = cbuf;                                         // 2 x (2*kT + 2) doubles
+  double* cy = cbuf + 2 * (2 * kT + 2);                      // 2 x (2*kT + 2) doubles; both 16-byte aligned
+  double d = __shfl_sync(0xffffffffu, a[0], 0);
+  double r = fast_rsqrt(d);
+  potrf_phase<32>(a, lane, 0, cx, cy, out, d, r, ok, rdiag_out);
+  potrf_phase<24>(a, lane, 8, cx, cy, out, d, r, ok, rdiag_out);
+  potrf_phase<16>(a, lane, 16, cx, cy, out, d, r, ok, rdiag_out);
+  potrf_phase<8>(a, lane, 24, cx, cy, out, d, r, ok, rdiag_out);
+  return ok;
+}
+
 struct CholParams {
   const double* H;   // [n][n] fp64, lower triangle valid
   const double* b;   // [n]
@@ -177,7 +230,7 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
   __shared__ double s_Lkk[kT][kTP];
   __shared__ double s_rdiag[kT];
   __shared__ double s_vec[kT];
-  __shared__ double s_col[2 * kT];
+  __shared__ __align__(16) double s_col[4 * (2 * kT + 2)];
   __shared__ int s_act[kCholThreads];                // tile rows with a nonzero tile in panel k (ascending; the rhs row nt is always last)
   __shared__ int s_wc[kCholWarps];
   __shared__ int s_nact;
@@ -380,11 +433,9 @@ __global__ void __launch_bounds__(kCholThreads, 1) chol_cluster_kernel(CholParam
         double a[kT], rd;
 #pragma unroll
         for (int c = 0; c < kT; c++) a[c] = s_T[lane][c];
-        if (!warp_potrf(a, lane, s_col, rd) && lane == 0) *p.fail = 1;
-        if (p.timing && lane == 0) p.timing[8 + 8 * k + 6] = gtimer();
         __syncwarp();
-#pragma unroll
-        for (int c = 0; c < kT; c++) s_T[lane][c] = (c <= lane) ? a[c] : 0.0;
+        if (!warp_potrf_compact(a, lane, s_col, s_T, rd) && lane == 0) *p.fail = 1;   // writes L into s_T
+        if (p.timing && lane == 0) p.timing[8 + 8 * k + 6] = gtimer();
         __syncwarp();
 #pragma unroll 8
         for (int r = 0; r < kT; r++) stcg(Ct + (size_t)r * ld + lane, s_T[r][lane]);
@@ -541,59 +592,6 @@ __device__ __forceinline__ size_t sys_index(int r, int c, int n, bool diag_tile)
     if (diag_tile) return (size_t)c * n + r;
   }
   return (size_t)-1;
-}
-
-// Cholesky of a 32x32 tile, one row per lane, in ~300 instructions instead of the ~1800 straight-line ones of warp_potrf.  ncu on the
-// resident kernel (profiles/r2_chol_resident_stalls.txt): 40 % of the samples inside the unrolled potrf are "no instruction" -- the code is
-// executed once per SM and its delivery from the GPC-level instruction cache, not its dependent chain, sets the pace (2.9 us on an idle
-// GPC, 5.3 us while the other 15 SMs fetch code of their own).  Here the row is shifted down one register per column, so a[0] is always
-// the pivot column and all register indices are static inside a rolled loop; four loops of eight columns with widths 32/24/16/8 keep
-// the extra arithmetic at 608 instead of 496 DFMAs.  The pivot column is published twice (offset by one double) so that the operands
-// of the rank-1 update can be fetched with aligned 16-byte loads whatever the parity of the column.  Per element the operations and
-// their order are those of warp_potrf: identical bits.  out[lane][k] receives L (zeros above the diagonal).
-template <int W>
-__device__ __forceinline__ void potrf_phase(double (&a)[kT], int lane, int k0, double* cx, double* cy, double (*out)[kTP], double& d, double& r, bool& ok,
-                                            double& rdiag_out) {
-#pragma unroll 1
-  for (int k = k0; k < k0 + 8; k++) {
-    if (!(d > 0.0)) ok = false;
-    const double l = (lane == k) ? d * r : a[0] * r;
-    if (lane == k) rdiag_out = r;
-    out[lane][k] = (lane >= k) ? l : 0.0;
-    double* bx = cx + (k & 1) * (2 * kT + 2);               // double-buffered over k: no second barrier per column
-    double* by = cy + (k & 1) * (2 * kT + 2);
-    bx[lane] = l;                                            // bx[t]     = l of row t
-    by[lane + 1] = l;                                        // by[t + 1] = l of row t
-    __syncwarp();
-    const double* ck = ((k + 1) & 1) ? (by + k + 2) : (bx + k + 1);   // ck[m] = l of row k+1+m, 16-byte aligned either way
-    const double2 c01 = *reinterpret_cast<const double2*>(ck);
-    const double a0 = a[1] - l * c01.x;
-    d = __shfl_sync(0xffffffffu, a0, (k + 1) & 31);
-    r = fast_rsqrt(d);
-    if (W > 2) a[1] = a[2] - l * c01.y;
-#pragma unroll
-    for (int m = 2; m + 1 < W - 1; m += 2) {
-      const double2 c = *reinterpret_cast<const double2*>(ck + m);
-      a[m] = a[m + 1] - l * c.x;
-      a[m + 1] = a[m + 2] - l * c.y;
-    }
-    if (((W - 1) & 1) && W > 3) a[W - 2] = a[W - 1] - l * ck[W - 2];   // odd count: one element left (W - 1 updates in total)
-    a[0] = a0;
-  }
-}
-
-__device__ __forceinline__ bool warp_potrf_compact(double (&a)[kT], int lane, double* cbuf, double (*out)[kTP], double& rdiag_out) {
-  bool ok = true;
-  rdiag_out = 0.0;
-  double* cx = cbuf;                                         // 2 x (2*kT + 2) doubles
-  double* cy = cbuf + 2 * (2 * kT + 2);                      // 2 x (2*kT + 2) doubles; both 16-byte aligned
-  double d = __shfl_sync(0xffffffffu, a[0], 0);
-  double r = fast_rsqrt(d);
-  potrf_phase<32>(a, lane, 0, cx, cy, out, d, r, ok, rdiag_out);
-  potrf_phase<24>(a, lane, 8, cx, cy, out, d, r, ok, rdiag_out);
-  potrf_phase<16>(a, lane, 16, cx, cy, out, d, r, ok, rdiag_out);
-  potrf_phase<8>(a, lane, 24, cx, cy, out, d, r, ok, rdiag_out);
-  return ok;
 }
 
 #define RES_STAMP(col, slot) do { if (p.timing && lane == 0) p.timing[8 + 16 * (col) + (slot)] = gtimer(); } while (0)
