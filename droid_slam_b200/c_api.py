@@ -10,7 +10,7 @@ SYMBOLS = [
     "dba_projmap", "dba_reproject", "dba_cvx_upsample", "dba_frame_distance", "dba_depth_filter", "dba_iproj",
     "dba_ba_workspace_bytes", "dba_ba_system_offset", "dba_ba_system_bytes",
     "dba_ba_prepare", "dba_ba_build", "dba_ba_solve", "dba_ba", "dba_ba_read_info", "dba_ba_p2p_signal",
-    "dba_solve_workspace_bytes", "dba_solve_spd",
+    "dba_solve_workspace_bytes", "dba_solve_spd", "dba_solve_tile_placement",
     "dba_update_workspace_bytes", "dba_update_forward", "dba_conv_nhwc", "dba_proximity_workspace_bytes", "dba_proximity_edges",
 ]
 
@@ -72,6 +72,7 @@ def load():
     L.dba_solve_workspace_bytes.restype = ctypes.c_size_t
     L.dba_solve_workspace_bytes.argtypes = [ci]
     L.dba_solve_spd.argtypes = [vp, vp, ci, cf, cf, vp, vp, vp, ctypes.c_size_t, vp]
+    L.dba_solve_tile_placement.argtypes = [ci, vp, vp]
     L.dba_proximity_workspace_bytes.restype = ctypes.c_size_t
     L.dba_proximity_workspace_bytes.argtypes = [ci, ci, ci]
     L.dba_proximity_edges.argtypes = [vp, ci, ci, ci, vp, vp, ci, ci, ci, cf, ci, ci, vp, ci, vp, vp, ctypes.c_size_t, vp]

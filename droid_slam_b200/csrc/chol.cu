@@ -1112,6 +1112,19 @@ int chol_solve_launch(const double* H, const double* b, int n, double lm, double
 
 }  // namespace dba
 
+// host-side introspection of the resident kernel's tile placement (tests/test_oracle_cpu.py holds its invariants on the CPU):
+// map_i / map_j [128] receive the tile of every warp slot (0xFF = none); returns the cluster size, 0 if n is served by the barrier kernel
+extern "C" int dba_solve_tile_placement(int n, unsigned char* map_i, unsigned char* map_j) {
+  if (n <= 0 || !map_i || !map_j) return 0;
+  const int nt = (n + dba::kT - 1) / dba::kT;
+  if (nt > dba::kResMaxNt) return 0;
+  const int tiles = nt * (nt + 1) / 2 + nt;
+  int rcs = 1;
+  while (rcs * dba::kCholWarps < tiles || rcs < nt) rcs *= 2;
+  if (rcs > 16 || !dba::resident_tile_map(nt, rcs, map_i, map_j)) return 0;
+  return rcs;
+}
+
 // standalone entry (used by the solver tests and by callers that already hold a reduced system)
 extern "C" size_t dba_solve_workspace_bytes(int n) { return dba::chol_workspace_bytes(n) + 64; }
 

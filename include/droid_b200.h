@@ -247,6 +247,9 @@ int dba_conv_nhwc(const void* src0, int c0, int stride0, const void* src1, int c
 size_t dba_solve_workspace_bytes(int n);
 int dba_solve_spd(const double* H, const double* b, int n, float lm, float ep, float* x, int* fail_flag_device,
                   void* workspace, size_t workspace_bytes, dba_stream_t stream);
+/* host only: where the resident-tile Cholesky (n <= 448) places its tiles -- map_i / map_j [128]: tile (i, j) of warp slot 8*cta + warp
+ * (i == number of tile rows: a right-hand-side piece; 0xFF: none).  Returns the cluster size, 0 when n is served by the barrier kernel. */
+int dba_solve_tile_placement(int n, unsigned char* map_i, unsigned char* map_j);
 
 #ifdef __cplusplus
 }
