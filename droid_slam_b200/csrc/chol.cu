@@ -2,10 +2,14 @@
 //
 // Replaces the reference's host-side SparseBlock::solve (src/droid_kernels.cu:1201-1222: Eigen::SimplicialLLT in
 // fp64 on the CPU behind two PCIe round trips).  Same contract: fp64 arithmetic, a non-positive pivot means
-// "not SPD" and yields x = 0.
+// "not SPD" and yields x = 0.  Two kernels, both one thread-block CLUSTER of up to 16 CTAs (16 SMs of one GPC), 32x32 fp64 tiles:
 //
-// One thread-block CLUSTER (up to 16 CTAs, i.e. up to 16 SMs of one GPC) runs a right-looking tiled Cholesky with
-// 32x32 fp64 tiles that live in global memory (L2 resident: 6P x 6P doubles is 1.5 MB for P = 71).  Per panel k:
+//  * chol_resident_kernel (n <= 448, i.e. <= 14 tile rows: frontend windows, the 72-keyframe metric window) -- every tile has one owner
+//    warp for the whole factorisation and lives in its registers; tiles are handed over through global memory (L2) WITHOUT flags, fences
+//    or barriers: every output location is pre-filled with a NaN bit pattern no arithmetic produces and a consumer re-reads a tile until no
+//    element is that sentinel.  See the comment block above the kernel and DESIGN.md 4.4 for the measurements that led there (every
+//    acquire ends in CCTL.IVALL and makes the next global loads ~10x slower; the unrolled potrf was bound by instruction delivery).
+//  * chol_cluster_kernel (larger systems) -- right-looking tiled Cholesky with the tiles in global memory (L2 resident).  Per panel k:
 //     TRSM of the column-k tiles (one warp per tile, lane = row, forward substitution against L_kk in shared memory)
 //       -- cluster barrier --
 //     trailing update A_ij -= L_ik L_jk^T: one warp per tile with an 8x4 register block per lane (operands staged in the
@@ -14,17 +18,18 @@
 //     broadcast through shared memory) while every other warp of the cluster works on the remaining tiles; a spare
 //     warp inverts L_kk for the backward pass
 //       -- cluster barrier --
-// i.e. two hardware cluster barriers per panel instead of kernel launches or grid-wide syncs.
-// ENVELOPE: the reduced pose system of a sliding-window / proximity factor graph is block banded (pose a couples to pose b only
-// through a common source frame), and a Cholesky factor never fills in left of a row's first nonzero.  The load phase records, per
-// 32-row tile row, the first structurally nonzero tile column (`first`); TRSM, trailing updates and the backward substitution then
-// skip every tile outside that envelope.  A dense system (the 72-keyframe metric window) does the same work as before; the global-BA
-// configs (6P = 2394 ... 5994, half bandwidth ~150) drop from O(n^3) to O(n b^2) -- what Eigen's sparse LLT does for the reference.
+//    The barriers are acquire-free (cluster_sync_light: relaxed mbarrier arrivals over distributed shared memory behind a release
+//    store per thread), all exchanged data is st.cg / ld.cg.
+// ENVELOPE (chol_cluster_kernel): the reduced pose system of a sliding-window / proximity factor graph is block banded (pose a couples to
+// pose b only through a common source frame), and a Cholesky factor never fills in left of a row's first nonzero.  The load phase
+// records, per 32-row tile row, the first structurally nonzero tile column (`first`); TRSM, trailing updates and the backward
+// substitution then skip every tile outside that envelope: the global-BA configs (6P = 2394 ... 5994, half bandwidth ~150) drop from
+// O(n^3) to O(n b^2) -- what Eigen's sparse LLT does for the reference.
 // The right-hand side rides along as an extra tile row, so L^-1 b comes out of the factorisation for free; the
 // backward substitution uses the inverted diagonal tiles and runs in CTA 0.
-// (B200 note, measured: a dependent fp64 op costs ~10-20 cycles and a 64-bit warp shuffle pair is slower than a
-//  shared-memory broadcast, which is why the pivot column goes through shared memory and the pivot uses an fp32
-//  rsqrt seed + one Newton step -- 3e-14 relative, far below the fp32 rounding of the result.)
+// (B200 note, measured: a dependent fp64 op costs ~9 cycles, the fp64 pipe issues one warp instruction per ~2.3 cycles per SM
+//  sub-partition, and a 64-bit warp shuffle pair is slower than a shared-memory broadcast, which is why the pivot column goes through
+//  shared memory and the pivot uses an fp32 rsqrt seed + one Newton step -- 3e-14 relative, far below the fp32 rounding of the result.)
 #include "common.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
